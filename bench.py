@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py - sampled peptides/sec @ 200 Euler steps on synthetic 256-residue-pocket / 15-residue-peptide
+complexes (BASELINE.json metric), with the fused-IPA HBM roofline and the reference CPU path beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a path (torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+A "step" is ONE Euler iteration of FlowModel.sample over the whole per-GPU batch (denoiser evaluation
+= GAEncoder.forward, post-processing, manifold Euler update: flow_model.py:287-343), i.e. one pass of the
+hot path over one batch.  value = complexes / (200 x step time): inputs (encoder outputs, state) resident in
+HBM.  e2e = the same metric through the public API FlowModel.sample(batch, num_steps=200) starting from a
+pinned HOST batch, including encode, the 200 iterations and the device->host copy of the trajectory.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+EULER_STEPS = 200
+WEIGHT_SEED = 114514
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="complexes per GPU (cfg4: 512 over 8 GPUs)")
+    ap.add_argument("--pocket", type=int, default=256)
+    ap.add_argument("--peptide", type=int, default=15)
+    ap.add_argument("--cpu-batch", type=int, default=2, help="complexes in the bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-euler-steps", type=int, default=EULER_STEPS)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_model(device):
+    from pepflowww_b200.config import load_config
+    from pepflowww_b200.flow_model import FlowModel
+    from pepflowww_b200.utils import deterministic_state_dict
+    cfg, _ = load_config()
+    model = FlowModel(cfg.model).eval()
+    ckpt = os.environ.get("PEPFLOW_CKPT")
+    if ckpt and os.path.exists(ckpt):       # the reference's model1.pt / model2.pt load unchanged
+        from pepflowww_b200.utils import process_dic
+        model.load_state_dict(process_dic(torch.load(ckpt, map_location="cpu")["model"]))
+        weights = os.path.basename(ckpt)
+    else:
+        model.load_state_dict(deterministic_state_dict(model.state_dict(), WEIGHT_SEED))
+        weights = f"deterministic random init (seed {WEIGHT_SEED}, non-zero 'final' layers)"
+    return (model.to(device) if device is not None else model), weights
+
+
+def cpu_baseline(args, steps, warmup):
+    """The oracle port of the reference algorithm on the host cores: encode + `steps` Euler iterations of a
+    bounded sample (cpu_batch complexes of the same shape); 200-step time = encode + 200 x mean step."""
+    from oracle import pepflow_oracle as orc
+    from pepflowww_b200.constants import torsions_mask
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, _ = make_model(None)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    batch = synthetic_batch(args.cpu_batch, args.pocket, args.peptide, seed=0)
+    B, L = batch["aa"].shape
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        enc = orc.encode(sd, batch)
+        t_enc = time.perf_counter() - t0
+        g = torch.Generator().manual_seed(0)
+        gm = batch["generate_mask"]
+        q = torch.nn.functional.normalize(torch.randn(B, L, 4, generator=g), dim=-1)
+        state = (torch.where(gm[..., None, None], orc.quat_to_rot(q), enc["rotmats_1"]),
+                 torch.where(gm[..., None], torch.randn(B, L, 3, generator=g), enc["trans_1"]),
+                 torch.where(gm[..., None], torch.rand(B, L, 5, generator=g) * 6.2831853, enc["angles_1"]),
+                 enc["seqs_1"].clone(), orc.seq_to_simplex(enc["seqs_1"]))
+        noise0 = (state[1].clone(), state[4].clone())
+        gt = (enc["rotmats_1"], enc["trans_1"], enc["angles_1"], enc["seqs_1"])
+        ts = torch.linspace(1e-2, 1.0, EULER_STEPS)
+        times = []
+        for n in range(warmup + steps):
+            u = torch.rand(2, B, L, generator=g)
+            t0 = time.perf_counter()
+            pred = orc.ga_encoder_forward(sd, torch.ones(B, 1) * ts[n], state[0], state[1], state[2], state[3],
+                                          enc["node_embed"], enc["edge_embed"], gm.long(), batch["res_mask"].long())
+            clean = orc.denoise_postprocess(pred, gt, gm, u[0], torsions_mask)
+            state = orc.euler_update(state, clean, gt, noise0, gm, ts[n + 1] - ts[n], u[1], torsions_mask)
+            dt = time.perf_counter() - t0
+            if n >= warmup:
+                times.append(dt)
+    t_step = sum(times) / len(times)
+    value = B / (EULER_STEPS * t_step + t_enc)
+    return {"value": value, "unit": "peptides/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle port (torch CPU fp32) of FlowModel.sample: encode ({t_enc:.2f} s) + {steps} timed Euler "
+                      f"iterations after {warmup} warm-up ({t_step * 1e3:.0f} ms/step) on {B} complexes of "
+                      f"{args.pocket}+{args.peptide} residues, extrapolated to {EULER_STEPS} steps",
+            "ms_per_step": t_step * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+    cb = cpu_baseline(args, steps, warmup)
+    line = {"impl": "reference", "metric": "sampled peptides/sec @ 200 Euler steps, 256-res pocket", "value": cb["value"],
+            "unit": "peptides/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg4 shape: {args.pocket}-res pocket / {args.peptide}-res peptide, "
+                                   f"{EULER_STEPS} Euler steps; CPU sample of {args.cpu_batch} complexes"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "peptides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from pepflowww_b200 import _lib
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    from pepflowww_b200.utils import recursive_to
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    model, weights = make_model(dev)
+    B, K, W = args.batch, args.steps, max(args.warmup, 0)
+    # this rank's shard of independent complexes (weak scaling: B per GPU, no data-path collective)
+    host_batch = synthetic_batch(B, args.pocket, args.peptide, seed=0, first_index=rank * B)
+    host_batch = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
+    L = args.pocket + args.peptide
+    hbm_peak, tensor_peak, peak_src = measured_peaks()
+
+    # ---------------- device-resident timing of K Euler iterations
+    batch = recursive_to(host_batch, dev)
+    smp = model.sampler_init(batch, num_steps=EULER_STEPS, seed=1234 + rank)
+    torch.cuda.synchronize()
+    for n in range(W):
+        smp.step(n)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    _lib.reset_launch_count()
+    _lib.profile_read()
+    _lib.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for n in range(W, W + K):
+        smp.step(n % (EULER_STEPS - 1))
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count()
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+    clk = clocks.stop()
+    ms_step = max_over_ranks(ms_total / K)
+    value = n_gpus * B / (EULER_STEPS * ms_step / 1e3)
+
+    # roofline of the fused IPA attention kernel (256 L^2 + 21168 L bytes per complex)
+    ipa_ms, ipa_n = prof["ipa"]
+    edge_ms, edge_n = prof["edge"]
+    ipa_bytes = (256.0 * L * L + 21168.0 * L) * B
+    roofline = None
+    if ipa_n:
+        ach = ipa_bytes / (ipa_ms / ipa_n * 1e-3) / 1e9
+        roofline = {"kernel": "ipa_attention", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": ipa_ms / ipa_n, "launches": ipa_n, "share_of_step": ipa_ms / ms_total,
+                    "algorithmic_bytes_per_launch": ipa_bytes}
+    roofline_edge = None
+    if edge_n:
+        passes = 3 if _lib.get_option("edge_impl") == 1 else 1
+        flops = 172032.0 * L * L * B
+        ach = flops / (edge_ms / edge_n * 1e-3) / 1e12
+        roofline_edge = {"kernel": "edge_transition", "bound": "tensor" if passes == 3 else "fp32-fma",
+                         "achieved": ach, "peak": tensor_peak / passes, "unit": "TFLOP/s",
+                         "frac": ach / (tensor_peak / passes), "traffic": None, "peak_source": peak_src,
+                         "note": f"algorithmic fp32-equivalent FLOPs; peak = sustained bf16 / {passes} split-precision passes",
+                         "avg_launch_ms": edge_ms / edge_n, "launches": edge_n, "share_of_step": edge_ms / ms_total}
+
+    # ---------------- end to end through the public API, host batch -> host trajectory
+    e2e = None
+    if not args.no_e2e:
+        del smp
+        torch.cuda.empty_cache()
+        warm = model.sample(recursive_to(host_batch, dev), num_steps=2)   # warm the allocator / pinned paths
+        del warm
+        barrier()
+        t0 = time.perf_counter()
+        dev_batch = recursive_to(host_batch, dev)
+        traj = model.sample(dev_batch, num_steps=args.e2e_euler_steps, seed=99 + rank)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        wall = max_over_ranks(wall)
+        h2d = sum(v.numel() * v.element_size() for v in host_batch.values() if isinstance(v, torch.Tensor))
+        d2h = sum(v.numel() * v.element_size() for v in traj[0].values())
+        d2h = d2h * len(traj) - (len(traj) - 1) * sum(traj[0][k].numel() * traj[0][k].element_size()
+                                                      for k in ("rotmats_1", "trans_1", "angles_1", "seqs_1"))
+        scale = EULER_STEPS / args.e2e_euler_steps
+        e2e = {"value": n_gpus * B / (wall * scale), "unit": "peptides/s",
+               "h2d_bytes_per_step": h2d / args.e2e_euler_steps, "d2h_bytes_per_step": d2h / args.e2e_euler_steps,
+               "wall_s": wall, "euler_steps": args.e2e_euler_steps,
+               "api": "FlowModel.sample(batch, num_steps=%d): pinned host batch -> device, encode, Euler loop, "
+                      "trajectory -> host" % args.e2e_euler_steps}
+        del traj
+
+    cb = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(args, steps=3, warmup=1)
+    barrier()
+    if rank == 0:
+        line = {"metric": "sampled peptides/sec @ 200 Euler steps, 256-res pocket; IPA HBM GB/s vs peak",
+                "value": value, "unit": "peptides/s", "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"cfg4: {B} complexes/GPU x {n_gpus} GPU, {args.pocket}-res pocket / "
+                                       f"{args.peptide}-res peptide (L={L}), {EULER_STEPS} Euler steps",
+                           "step": "one Euler iteration (GAEncoder.forward + post-processing + manifold update) over "
+                                   "the per-GPU batch; value = complexes / (200 x step time)",
+                           "global_batch": B * n_gpus, "parallelism": f"complexes sharded over {n_gpus} GPU(s), no collective",
+                           "weights": weights,
+                           "l2": "inputs larger than L2 (pair tensor z = %.2f GB per pass)" % (B * L * L * 256 / 1e9),
+                           "kernels": {k: _lib.get_option(k) for k in ("edge_impl", "gemm_impl", "ipa_impl")}},
+                "clocks": clk, "gpu_launches": launches, "e2e": e2e, "roofline": roofline,
+                "roofline_edge_transition": roofline_edge, "cpu_baseline": cb}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+/*
+ * pepflow_b200.h  --  C ABI of libpepflow_b200.so (sm_100a), the drop-in boundary for the
+ * PepFlow flow-matching denoising hot path.
+ *
+ * The reference (Ced3-han/PepFlowww) has no FFI / operator registry: its boundary is the Python
+ * object API (FlowModel.forward/.sample, GAEncoder.forward, ...).  The host side of this repo
+ * (pepflowww_b200/*.py) keeps that object API and binds the entry points below with ctypes; each
+ * entry point names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer into caller-owned, contiguous memory (torch tensors);
+ *     fp32 unless the name says otherwise; `seqs` are int64; masks are fp32 {0,1};
+ *   - the last argument is the cudaStream_t (as void*) the work is enqueued on; calls are
+ *     asynchronous, re-entrant, allocate nothing and keep no mutable global state;
+ *   - return value: 0 = PF_OK, otherwise a pf_status (negative: argument errors; positive: the
+ *     cudaError_t of a failed launch).  pf_strerror() maps it to text.  No C++ exception crosses.
+ *   - shapes use B complexes, L residues, H=8 heads, C=128 hidden, PQ=8, PV=12, c_s=128, c_z=64
+ *     (configs/learn_angle.yaml:3-14).  The kernels are specialised to these constants;
+ *     pf_check_config() rejects anything else.
+ */
+#ifndef PEPFLOW_B200_H
+#define PEPFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pf_status {
+  PF_OK = 0,
+  PF_ERR_BAD_SHAPE = -1,
+  PF_ERR_BAD_CONFIG = -2,
+  PF_ERR_NULL_POINTER = -3,
+  PF_ERR_MISALIGNED = -4,
+  PF_ERR_WORKSPACE_TOO_SMALL = -5,
+  PF_ERR_NO_DEVICE = -6,
+  PF_ERR_BAD_OPTION = -7
+} pf_status;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int pf_version(void);                       /* ABI version (this header: 1)                   */
+const char* pf_strerror(int status);
+int pf_init(int device);                    /* opt kernels into >48 KB shared memory, query SMs */
+int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_points, int no_v_points,
+                    int tfmr_heads, int tfmr_layers);  /* configs/learn_angle.yaml:3-14        */
+/* Kernel variant switches (test seams, not multi-backend dispatch: every variant is sm_100a CUDA).
+ *   "edge_impl": 0 = fp32 CUDA-core kernel, 1 = 3xBF16 tensor-core kernel (default)
+ *   "gemm_impl": 0 = fp32 CUDA-core GEMM,   1 = 3xBF16 tensor-core GEMM (default)
+ *   "ipa_impl" : 0 = CUDA-core attention,   1 = tensor-core attention (default when available)  */
+int pf_set_option(const char* name, int value);
+int pf_get_option(const char* name);
+/* Launch counter: number of kernels this library has enqueued since the last reset. */
+int64_t pf_launch_count(void);
+void pf_reset_launch_count(void);
+
+/* In-situ kernel timing for bench.py's roofline: when enabled, CUDA events are recorded on the launch
+ * stream around every IPA-attention and edge-transition kernel.  pf_profile_read() synchronises the
+ * recorded events, returns the summed durations / launch counts since the last read, and resets. */
+int pf_profile_enable(int on);
+int pf_profile_read(double* ipa_ms, int64_t* ipa_launches, double* edge_ms, int64_t* edge_launches);
+
+/* ---- generic node-level ops --------------------------------------------------------------- */
+/* y[M,N] = act(x[M,K] W[N,K]^T + bias) (+ residual[M,N]) (* rowmask[M]).   act: 0 none, 1 ReLU.
+ * Replaces models_con/ipa_pytorch.py:116-181 (Linear) and the nn.Linear layers of ga.py:22-45. */
+int pf_linear(const float* x, const float* w, const float* bias, const float* residual, const float* rowmask,
+              float* y, int M, int K, int N, int act, void* stream);
+/* y = LayerNorm_128(a + b) * rowmask   (b, rowmask optional).  ga.py:104, ipa_pytorch.py:203-204. */
+int pf_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, const float* rowmask,
+                     float* y, int M, int N, void* stream);
+
+/* ---- K1: input feature mix (models_con/ga.py:94-95, utils.py:60-72, layers.py:104-113) ------ */
+/* x[B*L,629] = node_embed(128) | seq_emb[seqs](128) | time_emb(t_b)(128) | angular_enc(angles)(245) */
+int pf_mix_features(const float* node_embed, const float* seq_emb_table, const int64_t* seqs, const float* t,
+                    const float* time_freqs /*[64]*/, const float* angles, const float* ang_freqs /*[24]*/,
+                    float* x, int B, int L, void* stream);
+
+/* ---- K2/K3: invariant point attention (models_con/ipa_pytorch.py:316-484) ------------------- */
+/* proj[B*L,3744] = q(1024) | kv(2048, per head k(128)|v(128)) | q_pts(192) | kv_pts(480) from one
+ * concatenated Linear; pf_ipa_points moves the point outputs into the global frame
+ * (ipa_pytorch.py:360-387; Rigid.apply openfold/utils/rigid_utils.py:1124-1136) and writes
+ * pts[B*L, H, 28, 3] = (8 q points | 8 k points | 12 v points).  rot [B*L,9] row-major. */
+int pf_ipa_points(const float* proj, const float* rot, const float* trans, float* pts, int B, int L, void* stream);
+/* Fused attention core: logits (scalar qk + pair bias + point distances + mask), softmax over j,
+ * o, o_pt (back in the local frame, plus norms) and o_pair; writes feats[B*L,1536] in the
+ * reference's concat order (ipa_pytorch.py:475).  z [B,L,L,64] is read once.
+ * head_w = softplus(head_weights)*sqrt(1/108) precomputed by the caller ([8]). */
+int pf_ipa_attention(const float* proj, const float* pts, const float* z, const float* w_b, const float* b_b,
+                     const float* w_dz, const float* b_dz, const float* head_w, const float* rot,
+                     const float* trans, const float* mask, float* feats, int B, int L, void* stream);
+
+/* ---- K5: sequence transformer attention core (torch.nn.TransformerEncoderLayer, ga.py:53-62) - */
+/* qkv[B*L,384] (in_proj output) -> ctx[B*L,128]; 4 heads x 32, key-padding mask (mask==0 keys skipped). */
+int pf_seq_attention(const float* qkv, const float* mask, float* ctx, int B, int L, void* stream);
+
+/* ---- K7: backbone / rigid update (openfold/utils/rigid_utils.py:1039-1063,587-616,208-227,185-205) */
+/* Block 0: quat_in == NULL and rot_in holds the input rotation matrices (rot -> quat inside).
+ * upd[B*L,6]; mask[B*L]; writes quat_out[B*L,4] (unit), rot_out[B*L,9] = R(quat_out), trans_out. */
+int pf_rigid_update(const float* quat_in, const float* rot_in, const float* trans_in, const float* upd,
+                    const float* mask, float* quat_out, float* rot_out, float* trans_out, int n, void* stream);
+
+/* ---- K8: edge transition (models_con/ipa_pytorch.py:233-248 + ga.py:118) --------------------- */
+/* z_out = LN_64(W_f (MLP2([z,e_i,e_j]) + [z,e_i,e_j]) + b_f) * mask_i mask_j,  e = Linear_128->64(s).
+ * z_out may alias z_in.  Weights are the reference tensors: w_init[64,128], w1/w2[192,192], wf[64,192]. */
+size_t pf_edge_transition_workspace_bytes(int B, int L);
+int pf_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,
+                       const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
+                       const float* bf, const float* ln_g, const float* ln_b, const float* mask, float* z_out,
+                       void* workspace, size_t workspace_bytes, int B, int L, void* stream);
+
+/* ---- K9: heads epilogue (ga.py:124-125) ------------------------------------------------------ */
+int pf_mod_2pi(const float* x, float* y, int n, void* stream);          /* torch.remainder(x, 2*pi) */
+int pf_quat_to_rot(const float* quat, float* rot, int n, void* stream); /* rigid_utils.py:185-205   */
+
+/* ---- manifold maps (data/so3_utils.py:143-254,486-520; models_con/torus.py:5-26) -------------- */
+int pf_so3_log(const float* rot, float* rotvec, int n, void* stream);
+int pf_so3_exp(const float* rotvec, float* rot, int n, void* stream);
+/* out = base * Exp(t * Log(base^T mat)); t has one entry per `group` consecutive matrices. */
+int pf_so3_geodesic(const float* t, const float* mat, const float* base, float* out, int n, int group, void* stream);
+int pf_tor_geodesic(const float* t, const float* ang1, const float* ang0, float* out, int n, int group, int d,
+                    void* stream);
+
+/* ---- K10: one Euler iteration of FlowModel.sample (models_con/flow_model.py:291-343) ----------- */
+/* Post-process the denoiser output (where(generate_mask), categorical draw of residue types,
+ * torsion masking; :291-303) and write the clean prediction of this step.
+ *   uniforms: optional [n] injected U[0,1) for the categorical draw; NULL -> Philox(seed, counter). */
+int pf_denoise_post(const float* pred_rot, const float* pred_trans, const float* pred_ang, const float* logits,
+                    const float* rot1, const float* trans1, const float* ang1, const int64_t* seq1,
+                    const uint8_t* gen_mask, const float* torsions_mask /*[22,5]*/, const float* uniforms,
+                    uint64_t seed, uint64_t counter, float* clean_rot, float* clean_trans, float* clean_ang,
+                    int64_t* clean_seq, float* clean_simplex, int n, float simplex_k, void* stream);
+/* Euler update of the state on R^3 x SO(3) x T^5 x simplex (:316-333).  State tensors are updated
+ * into the *_out buffers (may alias the inputs). */
+int pf_euler_step(const float* rot_t, const float* trans_t, const float* ang_t, const float* simplex_t,
+                  const float* clean_rot, const float* clean_trans, const float* clean_ang,
+                  const int64_t* clean_seq, const float* trans0, const float* simplex0, const float* rot1,
+                  const float* trans1, const float* ang1, const int64_t* seq1, const uint8_t* gen_mask,
+                  const float* torsions_mask, const float* uniforms, uint64_t seed, uint64_t counter, float d_t,
+                  float* rot_out, float* trans_out, float* ang_out, int64_t* seq_out, float* simplex_out, int n,
+                  float simplex_k, void* stream);
+
+/* ---- composite: GAEncoder.forward (models_con/ga.py:87-127) ----------------------------------- */
+/* Weight table: device pointers to the reference state_dict tensors (fp32, contiguous), host array.
+ * Slot order is pf_ga_global_slot / pf_ga_block_slot below. */
+enum pf_ga_global_slot {
+  PF_G_MIX0_W = 0, PF_G_MIX0_B, PF_G_MIX2_W, PF_G_MIX2_B, PF_G_SEQ_EMB, PF_G_ANG_FREQS, PF_G_TIME_FREQS,
+  PF_G_SEQNET0_W, PF_G_SEQNET0_B, PF_G_SEQNET2_W, PF_G_SEQNET2_B, PF_G_SEQNET4_W, PF_G_SEQNET4_B,
+  PF_G_ANGNET0_W, PF_G_ANGNET0_B, PF_G_ANGNET2_W, PF_G_ANGNET2_B, PF_G_ANGNET4_W, PF_G_ANGNET4_B,
+  PF_G_NSLOTS
+};
+enum pf_ga_block_slot {
+  PF_B_PROJ_W = 0 /* [3744,128] = cat(linear_q, linear_kv, linear_q_points, linear_kv_points) */, PF_B_PROJ_B,
+  PF_B_LINB_W, PF_B_LINB_B, PF_B_DOWNZ_W, PF_B_DOWNZ_B, PF_B_HEAD_W /* softplus(head_weights)*sqrt(1/108) */,
+  PF_B_OUT_W, PF_B_OUT_B, PF_B_IPA_LN_G, PF_B_IPA_LN_B,
+  PF_B_T0_IN_W, PF_B_T0_IN_B, PF_B_T0_OUT_W, PF_B_T0_OUT_B, PF_B_T0_L1_W, PF_B_T0_L1_B, PF_B_T0_L2_W, PF_B_T0_L2_B,
+  PF_B_T0_N1_G, PF_B_T0_N1_B, PF_B_T0_N2_G, PF_B_T0_N2_B,
+  PF_B_T1_IN_W, PF_B_T1_IN_B, PF_B_T1_OUT_W, PF_B_T1_OUT_B, PF_B_T1_L1_W, PF_B_T1_L1_B, PF_B_T1_L2_W, PF_B_T1_L2_B,
+  PF_B_T1_N1_G, PF_B_T1_N1_B, PF_B_T1_N2_G, PF_B_T1_N2_B,
+  PF_B_POST_W, PF_B_POST_B, PF_B_NT1_W, PF_B_NT1_B, PF_B_NT2_W, PF_B_NT2_B, PF_B_NT3_W, PF_B_NT3_B,
+  PF_B_NT_LN_G, PF_B_NT_LN_B, PF_B_BB_W, PF_B_BB_B,
+  PF_B_ET_INIT_W, PF_B_ET_INIT_B, PF_B_ET_W1, PF_B_ET_B1, PF_B_ET_W2, PF_B_ET_B2, PF_B_ET_WF, PF_B_ET_BF,
+  PF_B_ET_LN_G, PF_B_ET_LN_B,
+  PF_B_NSLOTS
+};
+#define PF_MAX_BLOCKS 8
+typedef struct pf_ga_weights {
+  int32_t num_blocks;
+  int32_t reserved;
+  const float* g[PF_G_NSLOTS];
+  const float* blk[PF_MAX_BLOCKS][PF_B_NSLOTS];
+} pf_ga_weights;
+
+size_t pf_ga_encoder_workspace_bytes(int B, int L);
+/* t[B]; rot_t[B,L,9]; trans_t[B,L,3]; angles_t[B,L,5]; seqs_t[B,L] i64; node_embed[B,L,128];
+ * edge_embed[B,L,L,64] (not modified); res_mask[B,L] fp32.  Outputs: pred_rot[B,L,9], pred_trans[B,L,3],
+ * pred_angles[B,L,5] in [0,2pi), logits[B,L,20].  Optional node_out[B,L,128] (final node embedding). */
+int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* rot_t, const float* trans_t,
+                          const float* angles_t, const int64_t* seqs_t, const float* node_embed,
+                          const float* edge_embed, const float* res_mask, float* pred_rot, float* pred_trans,
+                          float* pred_angles, float* logits, float* node_out, void* workspace,
+                          size_t workspace_bytes, int B, int L, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEPFLOW_B200_H */

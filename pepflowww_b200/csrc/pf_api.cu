@@ -1,0 +1,283 @@
+// Library-level entry points and the composite GAEncoder.forward (models_con/ga.py:87-127):
+// the whole denoiser evaluation is chained here natively so the host makes ONE call per step and the
+// sequence can be captured in a CUDA graph.
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "pf_common.cuh"
+
+namespace pf {
+
+static std::atomic<int64_t> g_launches{0};
+static int g_num_sms = 148;
+static std::atomic<int> g_edge_impl{1}, g_gemm_impl{1}, g_ipa_impl{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static std::atomic<int> g_profile{0};
+static std::mutex g_prof_mu;
+static std::vector<cudaEvent_t> g_ev_pool;               // reusable events
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev[2];
+static cudaEvent_t g_open[2] = {nullptr, nullptr};
+
+static cudaEvent_t take_event() {
+  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void profile_begin(int c, cudaStream_t st) {
+  if (!g_profile.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_open[c] = take_event();
+  cudaEventRecord(g_open[c], st);
+}
+void profile_end(int c, cudaStream_t st) {
+  if (!g_profile.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_open[c]) return;
+  cudaEvent_t e = take_event();
+  cudaEventRecord(e, st);
+  g_ev[c].emplace_back(g_open[c], e);
+  g_open[c] = nullptr;
+}
+int num_sms() { return g_num_sms; }
+int opt_edge_impl() { return g_edge_impl.load(std::memory_order_relaxed); }
+int opt_gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
+int opt_ipa_impl() { return g_ipa_impl.load(std::memory_order_relaxed); }
+
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct GaWorkspace {
+  float *xmix, *s, *ta, *tb, *ya, *yb, *proj, *pts, *feats, *qkv, *ctx, *quat, *rot, *trans, *upd, *ang_raw, *zbuf;
+  void* edge_ws;
+  size_t edge_ws_bytes, total;
+};
+
+static GaWorkspace carve(void* base, int B, int L) {
+  const size_t M = (size_t)B * L;
+  unsigned char* p = static_cast<unsigned char*>(base);
+  size_t off = 0;
+  GaWorkspace w;
+  auto take = [&](size_t bytes) {
+    float* r = reinterpret_cast<float*>(p + off);
+    off += al(bytes);
+    return r;
+  };
+  w.xmix = take(M * NMIX * 4);
+  w.s = take(M * 128 * 4);
+  w.ta = take(M * 128 * 4);
+  w.tb = take(M * 128 * 4);
+  w.ya = take(M * 128 * 4);
+  w.yb = take(M * 128 * 4);
+  w.proj = take(M * NPROJ * 4);
+  w.pts = take(M * H * NPT * 3 * 4);
+  w.feats = take(M * NFEAT * 4);
+  w.qkv = take(M * 384 * 4);
+  w.ctx = take(M * 128 * 4);
+  w.quat = take(M * 4 * 4);
+  w.rot = take(M * 9 * 4);
+  w.trans = take(M * 3 * 4);
+  w.upd = take(M * 6 * 4);
+  w.ang_raw = take(M * 5 * 4);
+  w.zbuf = take(M * L * CZ * 4);
+  w.edge_ws_bytes = edge_workspace_bytes(B, L);
+  w.edge_ws = take(w.edge_ws_bytes);
+  w.total = off;
+  return w;
+}
+
+}  // namespace pf
+
+extern "C" {
+
+int pf_version(void) { return 1; }
+
+const char* pf_strerror(int status) {
+  switch (status) {
+    case PF_OK: return "ok";
+    case PF_ERR_BAD_SHAPE: return "bad shape";
+    case PF_ERR_BAD_CONFIG: return "unsupported model configuration (kernels are specialised to learn_angle.yaml)";
+    case PF_ERR_NULL_POINTER: return "null pointer";
+    case PF_ERR_MISALIGNED: return "pointer not 16-byte aligned";
+    case PF_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case PF_ERR_NO_DEVICE: return "no CUDA device";
+    case PF_ERR_BAD_OPTION: return "unknown option";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+  return "unknown pf_status";
+}
+
+int pf_init(int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return PF_ERR_NO_DEVICE;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int sms = 0;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  pf::g_num_sms = sms;
+  pf::node_kernels_init();
+  pf::ipa_kernels_init();
+  pf::edge_kernels_init();
+  e = cudaGetLastError();
+  return e == cudaSuccess ? PF_OK : static_cast<int>(e);
+}
+
+int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_points, int no_v_points, int tfmr_heads,
+                    int tfmr_layers) {
+  const bool ok = c_s == pf::CS && c_z == pf::CZ && c_hidden == pf::C && no_heads == pf::H &&
+                  no_qk_points == pf::PQ && no_v_points == pf::PV && tfmr_heads == 4 && tfmr_layers == 2;
+  return ok ? PF_OK : PF_ERR_BAD_CONFIG;
+}
+
+int pf_set_option(const char* name, int value) {
+  if (!name) return PF_ERR_NULL_POINTER;
+  if (!std::strcmp(name, "edge_impl") && (value == 0 || value == 1)) { pf::g_edge_impl = value; return PF_OK; }
+  if (!std::strcmp(name, "gemm_impl") && (value == 0 || value == 1)) { pf::g_gemm_impl = value; return PF_OK; }
+  if (!std::strcmp(name, "ipa_impl") && (value == 0)) { pf::g_ipa_impl = value; return PF_OK; }
+  return PF_ERR_BAD_OPTION;
+}
+
+int pf_get_option(const char* name) {
+  if (!name) return PF_ERR_NULL_POINTER;
+  if (!std::strcmp(name, "edge_impl")) return pf::opt_edge_impl();
+  if (!std::strcmp(name, "gemm_impl")) return pf::opt_gemm_impl();
+  if (!std::strcmp(name, "ipa_impl")) return pf::opt_ipa_impl();
+  return PF_ERR_BAD_OPTION;
+}
+
+int pf_profile_enable(int on) {
+  pf::g_profile.store(on ? 1 : 0);
+  return PF_OK;
+}
+
+int pf_profile_read(double* ipa_ms, int64_t* ipa_launches, double* edge_ms, int64_t* edge_launches) {
+  std::lock_guard<std::mutex> lk(pf::g_prof_mu);
+  double ms[2] = {0.0, 0.0};
+  int64_t cnt[2] = {0, 0};
+  for (int c = 0; c < 2; ++c) {
+    for (auto& pr : pf::g_ev[c]) {
+      cudaError_t e = cudaEventSynchronize(pr.second);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      float t = 0.f;
+      e = cudaEventElapsedTime(&t, pr.first, pr.second);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      ms[c] += t;
+      ++cnt[c];
+      pf::g_ev_pool.push_back(pr.first);
+      pf::g_ev_pool.push_back(pr.second);
+    }
+    pf::g_ev[c].clear();
+  }
+  if (ipa_ms) *ipa_ms = ms[0];
+  if (ipa_launches) *ipa_launches = cnt[0];
+  if (edge_ms) *edge_ms = ms[1];
+  if (edge_launches) *edge_launches = cnt[1];
+  return PF_OK;
+}
+
+int64_t pf_launch_count(void) { return pf::g_launches.load(); }
+void pf_reset_launch_count(void) { pf::g_launches.store(0); }
+
+size_t pf_ga_encoder_workspace_bytes(int B, int L) {
+  if (B <= 0 || L <= 0) return 256;
+  return pf::carve(nullptr, B, L).total;
+}
+
+int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* rot_t, const float* trans_t,
+                          const float* angles_t, const int64_t* seqs_t, const float* node_embed,
+                          const float* edge_embed, const float* res_mask, float* pred_rot, float* pred_trans,
+                          float* pred_angles, float* logits, float* node_out, void* workspace, size_t workspace_bytes,
+                          int B, int L, void* stream) {
+  using namespace pf;
+  PF_REQUIRE(w && t && rot_t && trans_t && angles_t && seqs_t && node_embed && edge_embed && res_mask && pred_rot &&
+                 pred_trans && pred_angles && logits && workspace, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(B >= 0 && L >= 0, PF_ERR_BAD_SHAPE);
+  PF_REQUIRE(w->num_blocks >= 1 && w->num_blocks <= PF_MAX_BLOCKS, PF_ERR_BAD_CONFIG);
+  if (B == 0 || L == 0) return PF_OK;
+  PF_REQUIRE(aligned16(workspace) && aligned16(edge_embed) && aligned16(node_embed), PF_ERR_MISALIGNED);
+  const GaWorkspace ws = carve(workspace, B, L);
+  PF_REQUIRE(workspace_bytes >= ws.total, PF_ERR_WORKSPACE_TOO_SMALL);
+  for (int i = 0; i < PF_G_NSLOTS; ++i) PF_REQUIRE(w->g[i], PF_ERR_NULL_POINTER);
+  cudaStream_t st = as_stream(stream);
+  const int M = B * L;
+  const int nb = w->num_blocks;
+
+  // K1: feature mix (ga.py:94-95)
+  PF_TRY(launch_mix_features(node_embed, w->g[PF_G_SEQ_EMB], seqs_t, t, w->g[PF_G_TIME_FREQS], angles_t,
+                             w->g[PF_G_ANG_FREQS], ws.xmix, B, L, st));
+  PF_TRY(launch_linear(ws.xmix, w->g[PF_G_MIX0_W], w->g[PF_G_MIX0_B], nullptr, nullptr, ws.ta, M, NMIX, 128, 1, st));
+  PF_TRY(launch_linear(ws.ta, w->g[PF_G_MIX2_W], w->g[PF_G_MIX2_B], nullptr, res_mask, ws.s, M, 128, 128, 0, st));
+
+  const float* rot = rot_t;      // block 0 uses the input rotation matrices as they are (ga.py:96)
+  const float* trans = trans_t;
+  const float* quat = nullptr;
+  const float* z = edge_embed;
+  for (int b = 0; b < nb; ++b) {
+    const float* const* W = w->blk[b];
+    const int n_need = (b < nb - 1) ? PF_B_NSLOTS : PF_B_ET_INIT_W;
+    for (int i = 0; i < n_need; ++i) PF_REQUIRE(W[i], PF_ERR_NULL_POINTER);
+    // IPA (ga.py:98-104)
+    PF_TRY(launch_linear(ws.s, W[PF_B_PROJ_W], W[PF_B_PROJ_B], nullptr, nullptr, ws.proj, M, 128, NPROJ, 0, st));
+    PF_TRY(launch_ipa_points(ws.proj, rot, trans, ws.pts, M, st));
+    IpaArgs ia{ws.proj, ws.pts, z, W[PF_B_LINB_W], W[PF_B_LINB_B], W[PF_B_DOWNZ_W], W[PF_B_DOWNZ_B], W[PF_B_HEAD_W],
+               rot, trans, res_mask, ws.feats, B, L};
+    PF_TRY(launch_ipa_attention(ia, st));
+    PF_TRY(launch_linear(ws.feats, W[PF_B_OUT_W], W[PF_B_OUT_B], nullptr, res_mask, ws.ta, M, NFEAT, 128, 0, st));
+    PF_TRY(launch_add_layernorm(ws.s, ws.ta, W[PF_B_IPA_LN_G], W[PF_B_IPA_LN_B], nullptr, ws.s, M, 128, st));
+    // sequence transformer, 2 post-norm layers (ga.py:105-106)
+    const float* x = ws.s;
+    float* outs[2] = {ws.ya, ws.yb};
+    for (int l = 0; l < 2; ++l) {
+      const int o = l == 0 ? PF_B_T0_IN_W : PF_B_T1_IN_W;
+      PF_TRY(launch_linear(x, W[o + 0], W[o + 1], nullptr, nullptr, ws.qkv, M, 128, 384, 0, st));
+      PF_TRY(launch_seq_attention(ws.qkv, res_mask, ws.ctx, B, L, st));
+      PF_TRY(launch_linear(ws.ctx, W[o + 2], W[o + 3], nullptr, nullptr, ws.ta, M, 128, 128, 0, st));
+      PF_TRY(launch_add_layernorm(x, ws.ta, W[o + 8], W[o + 9], nullptr, outs[l], M, 128, st));      // norm1
+      PF_TRY(launch_linear(outs[l], W[o + 4], W[o + 5], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));  // linear1+relu
+      PF_TRY(launch_linear(ws.tb, W[o + 6], W[o + 7], nullptr, nullptr, ws.ta, M, 128, 128, 0, st));     // linear2
+      PF_TRY(launch_add_layernorm(outs[l], ws.ta, W[o + 10], W[o + 11], nullptr, outs[l], M, 128, st)); // norm2
+      x = outs[l];
+    }
+    // s += post_tfmr(y)  (ga.py:107)
+    PF_TRY(launch_linear(x, W[PF_B_POST_W], W[PF_B_POST_B], ws.s, nullptr, ws.s, M, 128, 128, 0, st));
+    // node transition (ipa_pytorch.py:196-206) then mask (ga.py:108-109)
+    PF_TRY(launch_linear(ws.s, W[PF_B_NT1_W], W[PF_B_NT1_B], nullptr, nullptr, ws.ta, M, 128, 128, 1, st));
+    PF_TRY(launch_linear(ws.ta, W[PF_B_NT2_W], W[PF_B_NT2_B], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));
+    PF_TRY(launch_linear(ws.tb, W[PF_B_NT3_W], W[PF_B_NT3_B], nullptr, nullptr, ws.ta, M, 128, 128, 0, st));
+    PF_TRY(launch_add_layernorm(ws.s, ws.ta, W[PF_B_NT_LN_G], W[PF_B_NT_LN_B], res_mask, ws.s, M, 128, st));
+    // backbone update (ga.py:110-113)
+    PF_TRY(launch_linear(ws.s, W[PF_B_BB_W], W[PF_B_BB_B], nullptr, nullptr, ws.upd, M, 128, 6, 0, st));
+    const bool last = (b == nb - 1);
+    float* rot_o = last ? pred_rot : ws.rot;
+    float* trans_o = last ? pred_trans : ws.trans;
+    PF_TRY(launch_rigid_update(quat, quat ? nullptr : rot, trans, ws.upd, res_mask, ws.quat, rot_o, trans_o, M, st));
+    quat = ws.quat; rot = rot_o; trans = trans_o;
+    // edge transition (ga.py:115-118)
+    if (!last) {
+      PF_TRY(launch_edge_transition(ws.s, z, W[PF_B_ET_INIT_W], W[PF_B_ET_INIT_B], W[PF_B_ET_W1], W[PF_B_ET_B1],
+                                    W[PF_B_ET_W2], W[PF_B_ET_B2], W[PF_B_ET_WF], W[PF_B_ET_BF], W[PF_B_ET_LN_G],
+                                    W[PF_B_ET_LN_B], res_mask, ws.zbuf, ws.edge_ws, ws.edge_ws_bytes, B, L, st));
+      z = ws.zbuf;
+    }
+  }
+  // heads (ga.py:121-125)
+  PF_TRY(launch_linear(ws.s, w->g[PF_G_SEQNET0_W], w->g[PF_G_SEQNET0_B], nullptr, nullptr, ws.ta, M, 128, 128, 1, st));
+  PF_TRY(launch_linear(ws.ta, w->g[PF_G_SEQNET2_W], w->g[PF_G_SEQNET2_B], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));
+  PF_TRY(launch_linear(ws.tb, w->g[PF_G_SEQNET4_W], w->g[PF_G_SEQNET4_B], nullptr, nullptr, logits, M, 128, 20, 0, st));
+  PF_TRY(launch_linear(ws.s, w->g[PF_G_ANGNET0_W], w->g[PF_G_ANGNET0_B], nullptr, nullptr, ws.ta, M, 128, 128, 1, st));
+  PF_TRY(launch_linear(ws.ta, w->g[PF_G_ANGNET2_W], w->g[PF_G_ANGNET2_B], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));
+  PF_TRY(launch_linear(ws.tb, w->g[PF_G_ANGNET4_W], w->g[PF_G_ANGNET4_B], nullptr, nullptr, ws.ang_raw, M, 128, 5, 0, st));
+  PF_TRY(launch_mod_2pi(ws.ang_raw, pred_angles, M * 5, st));
+  if (node_out) {
+    cudaError_t e = cudaMemcpyAsync(node_out, ws.s, (size_t)M * 128 * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  return PF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// Shared declarations for libpepflow_b200.so (sm_100a).  Internal header - the public ABI is
+// include/pepflow_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pepflow_b200.h"
+
+namespace pf {
+
+// Model constants (configs/learn_angle.yaml:3-14 of the reference); kernels are specialised to them.
+constexpr int H = 8;        // IPA heads
+constexpr int C = 128;      // IPA hidden per head
+constexpr int PQ = 8;       // query/key points
+constexpr int PV = 12;      // value points
+constexpr int NPT = PQ + PQ + PV;  // 28 points per (residue, head) in the pts buffer: q | k | v
+constexpr int CS = 128;     // node channels
+constexpr int CZ = 64;      // pair channels
+constexpr int NPROJ = 3744; // q 1024 | kv 2048 | q_pts 192 | kv_pts 480
+constexpr int OFF_Q = 0, OFF_KV = 1024, OFF_QP = 3072, OFF_KVP = 3264;
+constexpr int NFEAT = 1536; // IPA concat width: o 1024 | o_pt xyz 288 | norms 96 | o_pair 128
+constexpr int NMIX = 629;   // 128 + 128 + 128 + 245
+constexpr float TWO_PI_F = 6.2831854820251465f;  // float(2*math.pi)
+
+void count_launch();
+// in-situ kernel timing (bench roofline): category 0 = IPA attention, 1 = edge transition
+void profile_begin(int category, cudaStream_t st);
+void profile_end(int category, cudaStream_t st);
+int num_sms();
+int opt_edge_impl();
+int opt_gemm_impl();
+int opt_ipa_impl();
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define PF_CHECK_LAUNCH()                                   \
+  do {                                                      \
+    pf::count_launch();                                     \
+    cudaError_t pf_e_ = cudaGetLastError();                 \
+    if (pf_e_ != cudaSuccess) return static_cast<int>(pf_e_); \
+  } while (0)
+
+#define PF_REQUIRE(cond, code) \
+  do {                         \
+    if (!(cond)) return (code); \
+  } while (0)
+
+#define PF_TRY(expr)              \
+  do {                            \
+    int pf_s_ = (expr);           \
+    if (pf_s_ != PF_OK) return pf_s_; \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// R(q) exactly as openfold/utils/rigid_utils.py:185-205 (no renormalisation inside).
+__device__ __forceinline__ void quat_to_rot_dev(float a, float b, float c, float d, float* R) {
+  R[0] = a * a + b * b - c * c - d * d; R[1] = 2.f * b * c - 2.f * a * d;     R[2] = 2.f * b * d + 2.f * a * c;
+  R[3] = 2.f * b * c + 2.f * a * d;     R[4] = a * a - b * b + c * c - d * d; R[5] = 2.f * c * d - 2.f * a * b;
+  R[6] = 2.f * b * d - 2.f * a * c;     R[7] = 2.f * c * d + 2.f * a * b;     R[8] = a * a - b * b - c * c + d * d;
+}
+
+// torch.remainder(x, 2*pi) for fp32 (sign of the divisor).
+__device__ __forceinline__ float mod_2pi(float x) {
+  float m = fmodf(x, TWO_PI_F);
+  if (m != 0.f && m < 0.f) m += TWO_PI_F;
+  return m;
+}
+
+// ---- internal launchers shared between translation units ---------------------------------------
+struct IpaArgs {
+  const float* proj;    // [B*L, 3744]
+  const float* pts;     // [B*L, H, 28, 3] global-frame points
+  const float* z;       // [B, L, L, 64]
+  const float* w_b;     // [8, 64]
+  const float* b_b;     // [8]
+  const float* w_dz;    // [16, 64]
+  const float* b_dz;    // [16]
+  const float* head_w;  // [8]  softplus(head_weights) * sqrt(1/108)
+  const float* rot;     // [B*L, 9]
+  const float* trans;   // [B*L, 3]
+  const float* mask;    // [B*L]
+  float* feats;         // [B*L, 1536]
+  int B, L;
+};
+int launch_linear(const float* x, const float* w, const float* bias, const float* residual, const float* rowmask,
+                  float* y, int M, int K, int N, int act, cudaStream_t st);
+int launch_linear_ld(const float* x, const float* w, int ldw, const float* bias, float* y, int M, int K, int N,
+                     cudaStream_t st);
+int launch_mix_features(const float* node, const float* emb, const int64_t* seqs, const float* t, const float* tfreq,
+                        const float* angles, const float* afreq, float* x, int B, int L, cudaStream_t st);
+int launch_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, const float* rowmask,
+                         float* y, int M, int N, cudaStream_t st);
+int launch_seq_attention(const float* qkv, const float* mask, float* ctx, int B, int L, cudaStream_t st);
+int launch_rigid_update(const float* quat_in, const float* rot_in, const float* trans_in, const float* upd,
+                        const float* mask, float* quat_out, float* rot_out, float* trans_out, int n, cudaStream_t st);
+int launch_ipa_points(const float* proj, const float* rot, const float* trans, float* pts, int rows, cudaStream_t st);
+int launch_mod_2pi(const float* x, float* y, int n, cudaStream_t st);
+int launch_quat_to_rot(const float* quat, float* rot, int n, cudaStream_t st);
+int launch_ipa_attention(const IpaArgs& a, cudaStream_t st);
+size_t edge_workspace_bytes(int B, int L);
+int launch_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,
+                           const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
+                           const float* bf, const float* ln_g, const float* ln_b, const float* mask, float* z_out,
+                           void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st);
+void node_kernels_init();
+void ipa_kernels_init();
+void edge_kernels_init();
+
+}  // namespace pf

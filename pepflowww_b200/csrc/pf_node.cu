@@ -1,0 +1,363 @@
+// Per-residue (O(L)) kernels of the denoiser: input feature mix, residual+LayerNorm, sequence
+// transformer attention core, rigid-frame update, IPA point projection into the global frame.
+#include "pf_common.cuh"
+
+namespace pf {
+
+// ---------------------------------------------------------------- K1: feature mix input
+// x[row, 0:629] = node_embed | seq_emb[seq] | [sin,cos](t*2056*w_i) | per angle [a, sin(a f), cos(a f)]
+// (models_con/ga.py:94, models_con/utils.py:60-72, pepflow/modules/common/layers.py:104-113)
+__global__ void mix_features_kernel(const float* __restrict__ node, const float* __restrict__ emb,
+                                    const int64_t* __restrict__ seqs, const float* __restrict__ t,
+                                    const float* __restrict__ tfreq, const float* __restrict__ angles,
+                                    const float* __restrict__ afreq, float* __restrict__ x, int B, int L) {
+  const size_t total = (size_t)B * L * NMIX;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % NMIX);
+    const size_t row = idx / NMIX;
+    float v;
+    if (col < 128) {
+      v = node[row * 128 + col];
+    } else if (col < 256) {
+      v = emb[seqs[row] * 128 + (col - 128)];
+    } else if (col < 384) {
+      const int i = col - 256;
+      const float tau = t[row / L] * 2056.0f;
+      const float arg = tau * tfreq[i & 63];
+      v = (i < 64) ? sinf(arg) : cosf(arg);
+    } else {
+      const int a = col - 384;
+      const int ai = a / 49, r = a % 49;
+      const float ang = angles[row * 5 + ai];
+      if (r == 0) v = ang;
+      else if (r <= 24) v = sinf(ang * afreq[r - 1]);
+      else v = cosf(ang * afreq[r - 25]);
+    }
+    x[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------- residual + LayerNorm (+ row mask)
+// one warp per row, N = 32 * VPL
+template <int VPL>
+__global__ void add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ rowmask, float* __restrict__ y, int M) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  constexpr int N = 32 * VPL;
+  float v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < VPL; ++e) {
+    const int c = lane + 32 * e;
+    v[e] = a[(size_t)warp * N + c] + (b ? b[(size_t)warp * N + c] : 0.f);
+    s += v[e];
+  }
+  const float mu = warp_sum(s) / N;
+  float q = 0.f;
+#pragma unroll
+  for (int e = 0; e < VPL; ++e) {
+    const float d = v[e] - mu;
+    q += d * d;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / N + 1e-5f);
+  const float rm = rowmask ? rowmask[warp] : 1.f;
+#pragma unroll
+  for (int e = 0; e < VPL; ++e) {
+    const int c = lane + 32 * e;
+    y[(size_t)warp * N + c] = ((v[e] - mu) * rstd * gamma[c] + beta[c]) * rm;
+  }
+}
+
+// ---------------------------------------------------------------- K5: transformer attention core
+// CTA = (head, complex); K/V of this head staged in smem; warp handles query rows i = warp, warp+8, ...
+// qkv row layout (torch in_proj): q(128) | k(128) | v(128), head h at columns h*32 .. h*32+31.
+constexpr int TFH = 4, TFD = 32;
+__global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restrict__ qkv,
+                                                            const float* __restrict__ mask,
+                                                            float* __restrict__ ctx, int L) {
+  extern __shared__ float smem[];
+  float* Ks = smem;                      // [L][33]
+  float* Vs = Ks + (size_t)L * 33;       // [L][33]
+  float* Ps = Vs + (size_t)L * 33;       // [8][L]
+  float* Qs = Ps + (size_t)8 * L;        // [8][32]
+  float* Ms = Qs + 8 * 32;               // [L]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* base = qkv + (size_t)b * L * 384;
+  for (int idx = tid; idx < L * 32; idx += 256) {
+    const int j = idx >> 5, c = idx & 31;
+    Ks[j * 33 + c] = base[(size_t)j * 384 + 128 + h * 32 + c];
+    Vs[j * 33 + c] = base[(size_t)j * 384 + 256 + h * 32 + c];
+  }
+  for (int j = tid; j < L; j += 256) Ms[j] = mask[(size_t)b * L + j];
+  __syncthreads();
+  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
+  float* P = Ps + (size_t)warp * L;
+  float* Q = Qs + warp * 32;
+  for (int i = warp; i < L; i += 8) {
+    Q[lane] = base[(size_t)i * 384 + h * 32 + lane];
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < L; j += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) s = fmaf(Q[c], Ks[j * 33 + c], s);
+      s = (Ms[j] != 0.f) ? s * scale : -INFINITY;
+      P[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) {
+      const float p = (mx == -INFINITY) ? 0.f : expf(P[j] - mx);
+      P[j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float o = 0.f;
+    for (int j = 0; j < L; ++j) o = fmaf(P[j], Vs[j * 33 + lane], o);
+    ctx[((size_t)b * L + i) * 128 + h * 32 + lane] = (sum > 0.f) ? o / sum : 0.f;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- K7: rigid update
+// rot -> quat at block 0: Shepperd's closed form as the start vector, refined by three power
+// iterations on K(R)/3 + I/3 whose dominant eigenvector is the reference's eigh answer
+// (openfold/utils/rigid_utils.py:208-227); the sign is free (R(q) and the update are sign-invariant).
+__device__ void rot_to_quat_dev(const float* R, float* q) {
+  const float xx = R[0], xy = R[1], xz = R[2], yx = R[3], yy = R[4], yz = R[5], zx = R[6], zy = R[7], zz = R[8];
+  float k[4][4] = {{xx + yy + zz, zy - yz, xz - zx, yx - xy},
+                   {zy - yz, xx - yy - zz, xy + yx, xz + zx},
+                   {xz - zx, xy + yx, yy - xx - zz, yz + zy},
+                   {yx - xy, xz + zx, yz + zy, zz - xx - yy}};
+  // Start from the column of M = K/3 + I/3 with the largest diagonal (for an exact rotation that
+  // column is already (4/3) q_best q, and max_i q_i^2 >= 1/4 keeps it away from zero).
+  int best = 0;
+  float bd = k[0][0];
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (k[i][i] > bd) { bd = k[i][i]; best = i; }
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = k[i][best] / 3.0f + (i == best ? 1.0f / 3.0f : 0.0f);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    float n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+    const float inv = rsqrtf(n2);
+    float u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = v[i] * inv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      v[i] = (k[i][0] * u[0] + k[i][1] * u[1] + k[i][2] * u[2] + k[i][3] * u[3]) / 3.0f + u[i] / 3.0f;
+  }
+  const float n = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = v[i] / n;
+}
+
+// q' = normalize(q + m * q (x) (0,v));  t' = t + m * R_old u   (rigid_utils.py:1039-1063,587-616,266-275)
+__global__ void rigid_update_kernel(const float* __restrict__ quat_in, const float* __restrict__ rot_in,
+                                    const float* __restrict__ trans_in, const float* __restrict__ upd,
+                                    const float* __restrict__ mask, float* __restrict__ quat_out,
+                                    float* __restrict__ rot_out, float* __restrict__ trans_out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float q[4], R[9];
+  if (quat_in) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q[e] = quat_in[(size_t)i * 4 + e];
+    quat_to_rot_dev(q[0], q[1], q[2], q[3], R);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) R[e] = rot_in[(size_t)i * 9 + e];
+    rot_to_quat_dev(R, q);
+  }
+  const float m = mask[i];
+  const float* u = upd + (size_t)i * 6;
+  const float x = u[0], y = u[1], z = u[2];
+  const float a = q[0], b = q[1], c = q[2], d = q[3];
+  float nq[4] = {a + m * (-b * x - c * y - d * z), b + m * (a * x + c * z - d * y),
+                 c + m * (a * y - b * z + d * x), d + m * (a * z + b * y - c * x)};
+  const float nn = sqrtf(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) nq[e] /= nn;
+  const float tx = u[3], ty = u[4], tz = u[5];
+  trans_out[(size_t)i * 3 + 0] = trans_in[(size_t)i * 3 + 0] + m * (R[0] * tx + R[1] * ty + R[2] * tz);
+  trans_out[(size_t)i * 3 + 1] = trans_in[(size_t)i * 3 + 1] + m * (R[3] * tx + R[4] * ty + R[5] * tz);
+  trans_out[(size_t)i * 3 + 2] = trans_in[(size_t)i * 3 + 2] + m * (R[6] * tx + R[7] * ty + R[8] * tz);
+  float Rn[9];
+  quat_to_rot_dev(nq[0], nq[1], nq[2], nq[3], Rn);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) quat_out[(size_t)i * 4 + e] = nq[e];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) rot_out[(size_t)i * 9 + e] = Rn[e];
+}
+
+__global__ void quat_to_rot_kernel(const float* __restrict__ quat, float* __restrict__ rot, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float R[9];
+  quat_to_rot_dev(quat[(size_t)i * 4], quat[(size_t)i * 4 + 1], quat[(size_t)i * 4 + 2], quat[(size_t)i * 4 + 3], R);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) rot[(size_t)i * 9 + e] = R[e];
+}
+
+__global__ void mod_2pi_kernel(const float* __restrict__ x, float* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = mod_2pi(x[i]);
+}
+
+// ---------------------------------------------------------------- K2 epilogue: points -> global frame
+// proj columns: q_pts at OFF_QP as [3][H][8], kv_pts at OFF_KVP as [3][H][20] (x|y|z planes, head-major,
+// models_con/ipa_pytorch.py:360-387).  pts[row][h][28][3] = R * local + t  (rigid_utils.py:1124-1136).
+__global__ void ipa_points_kernel(const float* __restrict__ proj, const float* __restrict__ rot,
+                                  const float* __restrict__ trans, float* __restrict__ pts, int rows) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t total = (size_t)rows * H * NPT;
+  if (idx >= total) return;
+  const int p = (int)(idx % NPT);
+  const int h = (int)((idx / NPT) % H);
+  const size_t row = idx / (NPT * H);
+  const float* pr = proj + row * NPROJ;
+  float lx, ly, lz;
+  if (p < PQ) {
+    const int o = OFF_QP + h * PQ + p;
+    lx = pr[o]; ly = pr[o + H * PQ]; lz = pr[o + 2 * H * PQ];
+  } else {
+    const int n = PQ + PV;
+    const int o = OFF_KVP + h * n + (p - PQ);
+    lx = pr[o]; ly = pr[o + H * n]; lz = pr[o + 2 * H * n];
+  }
+  const float* R = rot + row * 9;
+  const float* t = trans + row * 3;
+  float* out = pts + idx * 3;
+  out[0] = R[0] * lx + R[1] * ly + R[2] * lz + t[0];
+  out[1] = R[3] * lx + R[4] * ly + R[5] * lz + t[1];
+  out[2] = R[6] * lx + R[7] * ly + R[8] * lz + t[2];
+}
+
+// ---------------------------------------------------------------- launchers (internal)
+int launch_mix_features(const float* node, const float* emb, const int64_t* seqs, const float* t, const float* tfreq,
+                        const float* angles, const float* afreq, float* x, int B, int L, cudaStream_t st) {
+  const size_t total = (size_t)B * L * NMIX;
+  if (total == 0) return PF_OK;
+  const int blocks = (int)min((size_t)(num_sms() * 8), (total + 255) / 256);
+  mix_features_kernel<<<blocks, 256, 0, st>>>(node, emb, seqs, t, tfreq, angles, afreq, x, B, L);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+int launch_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, const float* rowmask,
+                         float* y, int M, int N, cudaStream_t st) {
+  if (M == 0) return PF_OK;
+  const int blocks = (M + 7) / 8;
+  if (N == 128) add_layernorm_kernel<4><<<blocks, 256, 0, st>>>(a, b, gamma, beta, rowmask, y, M);
+  else if (N == 64) add_layernorm_kernel<2><<<blocks, 256, 0, st>>>(a, b, gamma, beta, rowmask, y, M);
+  else return PF_ERR_BAD_SHAPE;
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+size_t seq_attention_smem(int L) { return ((size_t)L * 33 * 2 + (size_t)8 * L + 8 * 32 + L) * sizeof(float); }
+
+int launch_seq_attention(const float* qkv, const float* mask, float* ctx, int B, int L, cudaStream_t st) {
+  if (B == 0 || L == 0) return PF_OK;
+  const size_t smem = seq_attention_smem(L);
+  if (smem > 227 * 1024) return PF_ERR_BAD_SHAPE;  // L <= ~780
+  seq_attention_kernel<<<dim3(TFH, B), 256, smem, st>>>(qkv, mask, ctx, L);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+int launch_rigid_update(const float* quat_in, const float* rot_in, const float* trans_in, const float* upd,
+                        const float* mask, float* quat_out, float* rot_out, float* trans_out, int n, cudaStream_t st) {
+  if (n == 0) return PF_OK;
+  rigid_update_kernel<<<(n + 127) / 128, 128, 0, st>>>(quat_in, rot_in, trans_in, upd, mask, quat_out, rot_out,
+                                                       trans_out, n);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+int launch_ipa_points(const float* proj, const float* rot, const float* trans, float* pts, int rows, cudaStream_t st) {
+  const size_t total = (size_t)rows * H * NPT;
+  if (total == 0) return PF_OK;
+  ipa_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(proj, rot, trans, pts, rows);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+int launch_mod_2pi(const float* x, float* y, int n, cudaStream_t st) {
+  if (n == 0) return PF_OK;
+  mod_2pi_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, y, n);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+int launch_quat_to_rot(const float* quat, float* rot, int n, cudaStream_t st) {
+  if (n == 0) return PF_OK;
+  quat_to_rot_kernel<<<(n + 255) / 256, 256, 0, st>>>(quat, rot, n);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+void node_kernels_init() {
+  cudaFuncSetAttribute(seq_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+}  // namespace pf
+
+// ---------------------------------------------------------------- C ABI
+extern "C" {
+
+int pf_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, const float* rowmask,
+                     float* y, int M, int N, void* stream) {
+  PF_REQUIRE(a && gamma && beta && y, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(M >= 0, PF_ERR_BAD_SHAPE);
+  return pf::launch_add_layernorm(a, b, gamma, beta, rowmask, y, M, N, pf::as_stream(stream));
+}
+
+int pf_mix_features(const float* node_embed, const float* seq_emb_table, const int64_t* seqs, const float* t,
+                    const float* time_freqs, const float* angles, const float* ang_freqs, float* x, int B, int L,
+                    void* stream) {
+  PF_REQUIRE(node_embed && seq_emb_table && seqs && t && time_freqs && angles && ang_freqs && x, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(B >= 0 && L >= 0, PF_ERR_BAD_SHAPE);
+  return pf::launch_mix_features(node_embed, seq_emb_table, seqs, t, time_freqs, angles, ang_freqs, x, B, L,
+                                 pf::as_stream(stream));
+}
+
+int pf_ipa_points(const float* proj, const float* rot, const float* trans, float* pts, int B, int L, void* stream) {
+  PF_REQUIRE(proj && rot && trans && pts, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(B >= 0 && L >= 0, PF_ERR_BAD_SHAPE);
+  return pf::launch_ipa_points(proj, rot, trans, pts, B * L, pf::as_stream(stream));
+}
+
+int pf_seq_attention(const float* qkv, const float* mask, float* ctx, int B, int L, void* stream) {
+  PF_REQUIRE(qkv && mask && ctx, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(B >= 0 && L >= 0, PF_ERR_BAD_SHAPE);
+  return pf::launch_seq_attention(qkv, mask, ctx, B, L, pf::as_stream(stream));
+}
+
+int pf_rigid_update(const float* quat_in, const float* rot_in, const float* trans_in, const float* upd,
+                    const float* mask, float* quat_out, float* rot_out, float* trans_out, int n, void* stream) {
+  PF_REQUIRE((quat_in || rot_in) && trans_in && upd && mask && quat_out && rot_out && trans_out, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(n >= 0, PF_ERR_BAD_SHAPE);
+  return pf::launch_rigid_update(quat_in, rot_in, trans_in, upd, mask, quat_out, rot_out, trans_out, n,
+                                 pf::as_stream(stream));
+}
+
+int pf_mod_2pi(const float* x, float* y, int n, void* stream) {
+  PF_REQUIRE(x && y, PF_ERR_NULL_POINTER);
+  return pf::launch_mod_2pi(x, y, n, pf::as_stream(stream));
+}
+
+int pf_quat_to_rot(const float* quat, float* rot, int n, void* stream) {
+  PF_REQUIRE(quat && rot, PF_ERR_NULL_POINTER);
+  return pf::launch_quat_to_rot(quat, rot, n, pf::as_stream(stream));
+}
+
+}  // extern "C"

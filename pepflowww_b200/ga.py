@@ -1,0 +1,141 @@
+"""GAEncoder: the per-step SE(3) denoiser (reference: models_con/ga.py:15-127), same constructor, parameter
+names and forward signature.  forward() makes ONE C-ABI call (pf_ga_encoder_forward) that chains every
+kernel of the six blocks natively on torch's current stream.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from . import ipa as ipa_pytorch
+from .layers import AngularEncoding
+from .utils_time import get_time_embedding, time_frequencies
+
+
+class GAEncoder(nn.Module):
+    def __init__(self, ipa_conf):
+        super().__init__()
+        self._ipa_conf = ipa_conf
+        c_s = ipa_conf.c_s
+        _lib.check(_lib.load().pf_check_config(ipa_conf.c_s, ipa_conf.c_z, ipa_conf.c_hidden, ipa_conf.no_heads,
+                                               ipa_conf.no_qk_points, ipa_conf.no_v_points,
+                                               ipa_conf.seq_tfmr_num_heads, ipa_conf.seq_tfmr_num_layers))
+        if not 1 <= ipa_conf.num_blocks <= _lib.PF_MAX_BLOCKS:
+            raise ValueError("num_blocks must be in [1, %d]" % _lib.PF_MAX_BLOCKS)
+        self.angles_embedder = AngularEncoding(num_funcs=12)
+        self.angle_net = nn.Sequential(nn.Linear(c_s, c_s), nn.ReLU(), nn.Linear(c_s, c_s), nn.ReLU(), nn.Linear(c_s, 5))
+        self.current_seq_embedder = nn.Embedding(22, c_s)
+        self.seq_net = nn.Sequential(nn.Linear(c_s, c_s), nn.ReLU(), nn.Linear(c_s, c_s), nn.ReLU(), nn.Linear(c_s, 20))
+        self.res_feat_mixer = nn.Sequential(
+            nn.Linear(3 * c_s + self.angles_embedder.get_out_dim(in_dim=5), c_s), nn.ReLU(), nn.Linear(c_s, c_s))
+        self.feat_dim = c_s
+        self.trunk = nn.ModuleDict()
+        for b in range(ipa_conf.num_blocks):
+            self.trunk[f"ipa_{b}"] = ipa_pytorch.InvariantPointAttention(ipa_conf)
+            self.trunk[f"ipa_ln_{b}"] = nn.LayerNorm(c_s)
+            layer = torch.nn.TransformerEncoderLayer(d_model=c_s, nhead=ipa_conf.seq_tfmr_num_heads,
+                                                     dim_feedforward=c_s, batch_first=True, dropout=0.0,
+                                                     norm_first=False)
+            self.trunk[f"seq_tfmr_{b}"] = torch.nn.TransformerEncoder(layer, ipa_conf.seq_tfmr_num_layers,
+                                                                      enable_nested_tensor=False)
+            self.trunk[f"post_tfmr_{b}"] = ipa_pytorch.Linear(c_s, c_s, init="final")
+            self.trunk[f"node_transition_{b}"] = ipa_pytorch.StructureModuleTransition(c=c_s)
+            self.trunk[f"bb_update_{b}"] = ipa_pytorch.BackboneUpdate(c_s, use_rot_updates=True)
+            if b < ipa_conf.num_blocks - 1:
+                self.trunk[f"edge_transition_{b}"] = ipa_pytorch.EdgeTransition(
+                    node_embed_size=c_s, edge_embed_in=ipa_conf.c_z, edge_embed_out=ipa_conf.c_z)
+        self._pack = None
+        self._pack_key = None
+        self._workspace = None
+
+    # ------------------------------------------------------------------ weight table for the C ABI
+    def embed_t(self, timesteps, mask):
+        return get_time_embedding(timesteps[:, 0], self.feat_dim, max_positions=2056)[:, None, :].repeat(1, mask.shape[1], 1)
+
+    def _pack_signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    @torch.no_grad()
+    def packed_weights(self):
+        """(GaWeights struct, keep-alive list).  Rebuilt only when a parameter changed."""
+        key = self._pack_signature()
+        if self._pack is not None and key == self._pack_key:
+            return self._pack
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GAEncoder: parameters must be on a CUDA device (no CPU fallback)")
+        keep = []
+
+        def P(t):
+            t = t.detach().to(torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.GaWeights()
+        w.num_blocks = self._ipa_conf.num_blocks
+        g = dict(MIX0_W=self.res_feat_mixer[0].weight, MIX0_B=self.res_feat_mixer[0].bias,
+                 MIX2_W=self.res_feat_mixer[2].weight, MIX2_B=self.res_feat_mixer[2].bias,
+                 SEQ_EMB=self.current_seq_embedder.weight, ANG_FREQS=self.angles_embedder.freq_bands,
+                 TIME_FREQS=time_frequencies(self.feat_dim, 2056).to(dev))
+        for name, net in (("SEQNET", self.seq_net), ("ANGNET", self.angle_net)):
+            for i in (0, 2, 4):
+                g[f"{name}{i}_W"], g[f"{name}{i}_B"] = net[i].weight, net[i].bias
+        for i, name in enumerate(_lib.G_SLOTS):
+            w.g[i] = P(g[name])
+        for b in range(self._ipa_conf.num_blocks):
+            ipa = self.trunk[f"ipa_{b}"]
+            pw, pb = ipa.packed_projection()
+            d = dict(PROJ_W=pw, PROJ_B=pb, LINB_W=ipa.linear_b.weight, LINB_B=ipa.linear_b.bias,
+                     DOWNZ_W=ipa.down_z.weight, DOWNZ_B=ipa.down_z.bias, HEAD_W=ipa.scaled_head_weights(),
+                     OUT_W=ipa.linear_out.weight, OUT_B=ipa.linear_out.bias,
+                     IPA_LN_G=self.trunk[f"ipa_ln_{b}"].weight, IPA_LN_B=self.trunk[f"ipa_ln_{b}"].bias)
+            for l, layer in enumerate(self.trunk[f"seq_tfmr_{b}"].layers):
+                d.update({f"T{l}_IN_W": layer.self_attn.in_proj_weight, f"T{l}_IN_B": layer.self_attn.in_proj_bias,
+                          f"T{l}_OUT_W": layer.self_attn.out_proj.weight, f"T{l}_OUT_B": layer.self_attn.out_proj.bias,
+                          f"T{l}_L1_W": layer.linear1.weight, f"T{l}_L1_B": layer.linear1.bias,
+                          f"T{l}_L2_W": layer.linear2.weight, f"T{l}_L2_B": layer.linear2.bias,
+                          f"T{l}_N1_G": layer.norm1.weight, f"T{l}_N1_B": layer.norm1.bias,
+                          f"T{l}_N2_G": layer.norm2.weight, f"T{l}_N2_B": layer.norm2.bias})
+            nt = self.trunk[f"node_transition_{b}"]
+            d.update(POST_W=self.trunk[f"post_tfmr_{b}"].weight, POST_B=self.trunk[f"post_tfmr_{b}"].bias,
+                     NT1_W=nt.linear_1.weight, NT1_B=nt.linear_1.bias, NT2_W=nt.linear_2.weight, NT2_B=nt.linear_2.bias,
+                     NT3_W=nt.linear_3.weight, NT3_B=nt.linear_3.bias, NT_LN_G=nt.ln.weight, NT_LN_B=nt.ln.bias,
+                     BB_W=self.trunk[f"bb_update_{b}"].linear.weight, BB_B=self.trunk[f"bb_update_{b}"].linear.bias)
+            if f"edge_transition_{b}" in self.trunk:
+                et = self.trunk[f"edge_transition_{b}"]
+                d.update(ET_INIT_W=et.initial_embed.weight, ET_INIT_B=et.initial_embed.bias,
+                         ET_W1=et.trunk[0].weight, ET_B1=et.trunk[0].bias, ET_W2=et.trunk[2].weight,
+                         ET_B2=et.trunk[2].bias, ET_WF=et.final_layer.weight, ET_BF=et.final_layer.bias,
+                         ET_LN_G=et.layer_norm.weight, ET_LN_B=et.layer_norm.bias)
+            for i, name in enumerate(_lib.B_SLOTS):
+                w.blk[b][i] = P(d[name]) if name in d else None
+        self._pack, self._pack_key = (w, keep), key
+        return self._pack
+
+    def workspace(self, B, L, device):
+        need = ops.ga_encoder_workspace_bytes(B, L)
+        ws = self._workspace
+        if ws is None or ws.numel() < need or ws.device != device:
+            self._workspace = None
+            ws = torch.empty(need, device=device, dtype=torch.uint8)
+            self._workspace = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, t, rotmats_t, trans_t, angles_t, seqs_t, node_embed, edge_embed, generate_mask, res_mask):
+        """t [B,1]; rotmats_t [B,L,3,3]; trans_t [B,L,3]; angles_t [B,L,5]; seqs_t [B,L] i64;
+        node_embed [B,L,128]; edge_embed [B,L,L,64]; masks [B,L] (long).  generate_mask is unused by the
+        network, exactly as in the reference (ga.py:87).  Returns (rotmats [B,L,3,3], trans, angles, logits)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("GAEncoder.forward runs the inference kernels; wrap the call in torch.no_grad() "
+                               "(the autograd training path is GAEncoder.forward_autograd)")
+        B, L = seqs_t.shape
+        dev = edge_embed.device
+        w, _keep = self.packed_weights()
+        ws = self.workspace(B, L, dev)
+        f = lambda x: x.to(torch.float32).contiguous()
+        return ops.ga_encoder_forward(w, f(t).reshape(B), f(rotmats_t), f(trans_t), f(angles_t),
+                                      seqs_t.to(torch.int64).contiguous(), f(node_embed), f(edge_embed),
+                                      f(res_mask), ws)

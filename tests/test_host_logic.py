@@ -1,0 +1,84 @@
+"""CPU: host-side logic - batch schema, collate, embedders against the reference's golden outputs,
+categorical sampler against the oracle, checkpoint key handling, fresh-init conventions."""
+import numpy as np
+import torch
+
+from oracle import pepflow_oracle as orc
+from tests.conftest import load_golden, rel_err
+
+
+def test_synthetic_batch_schema():
+    from pepflowww_b200.pep_dataloader import PaddingCollate, SyntheticPepDataset, synthetic_batch
+    ds = SyntheticPepDataset(num_complexes=3, len_pocket=10, len_peptide=4, seed=1)
+    item = ds[0]
+    assert item["aa"].shape == (14,) and item["pos_heavyatom"].shape == (14, 15, 3)
+    assert item["generate_mask"].sum() == 4 and not item["generate_mask"][:10].any()
+    assert item["chain_nb"][:10].eq(1).all() and item["chain_nb"][10:].eq(0).all()
+    ca = item["pos_heavyatom"][10:, 1]
+    assert ca.mean(0).abs().max() < 1e-4          # peptide CA centroid at the origin
+    b = PaddingCollate(eight=True)([ds[0], ds[1]])
+    assert b["aa"].shape == (2, 16) and b["res_mask"].sum() == 28 and (b["aa"][:, 14:] == 21).all()
+    b2 = synthetic_batch(2, 18, 5, seed=7)
+    g = load_golden("encode")
+    assert torch.equal(b2["aa"], g["aa"]) and torch.equal(b2["pos_heavyatom"], g["pos_heavyatom"])
+
+
+def test_embedders_match_reference_golden(state_dict):
+    from pepflowww_b200.config import load_config
+    from pepflowww_b200.flow_model import FlowModel
+    cfg, _ = load_config()
+    model = FlowModel(cfg.model).eval()
+    model.load_state_dict(state_dict)
+    g = load_golden("encode")
+    batch = {k: g[k] for k in ("aa", "pos_heavyatom", "mask_heavyatom", "res_nb", "chain_nb", "generate_mask",
+                               "res_mask", "torsion_angle", "torsion_angle_mask")}
+    with torch.no_grad():
+        r1, x1, a1, s1, node, edge = model.encode(batch)
+        model.edge_embedder.chunk_bytes = 1 << 16      # force the row-chunked path too
+        edge_chunked = model.edge_embedder(batch["aa"], batch["res_nb"], batch["chain_nb"], batch["pos_heavyatom"],
+                                           batch["mask_heavyatom"], structure_mask=~batch["generate_mask"],
+                                           sequence_mask=~batch["generate_mask"])
+    assert rel_err(r1, g["rotmats_1"]) < 1e-6
+    assert rel_err(node, g["node_embed"]) < 2e-5
+    assert rel_err(edge, g["edge_embed"]) < 2e-5
+    assert rel_err(edge_chunked, g["edge_embed"]) < 2e-5
+
+
+def test_categorical_matches_oracle():
+    from pepflowww_b200.layers import categorical_from_uniform
+    rng = np.random.default_rng(0)
+    p = torch.softmax(torch.from_numpy(rng.standard_normal((4, 50, 20)).astype(np.float32)) * 3, -1)
+    u = torch.from_numpy(rng.random((4, 50), dtype=np.float32))
+    assert torch.equal(categorical_from_uniform(p, u), orc.categorical_from_uniform(p, u))
+
+
+def test_process_dic_and_load(state_dict):
+    from pepflowww_b200.config import load_config
+    from pepflowww_b200.flow_model import FlowModel
+    from pepflowww_b200.utils import process_dic
+    cfg, _ = load_config()
+    ddp_style = {"module." + k: v for k, v in state_dict.items()}
+    model = FlowModel(cfg.model)
+    missing = model.load_state_dict(process_dic(ddp_style))
+    assert not missing.missing_keys and not missing.unexpected_keys
+
+
+def test_fresh_init_final_layers_are_zero():
+    from pepflowww_b200.config import load_config
+    from pepflowww_b200.flow_model import FlowModel
+    cfg, _ = load_config()
+    m = FlowModel(cfg.model)
+    t = m.ga_encoder.trunk
+    for name in ("ipa_0.linear_out", "post_tfmr_0", "node_transition_0.linear_3", "bb_update_0.linear",
+                 "edge_transition_0.final_layer"):
+        mod = t
+        for part in name.split("."):
+            mod = mod[part] if isinstance(mod, torch.nn.ModuleDict) else getattr(mod, part)
+        assert mod.weight.abs().sum() == 0 and mod.bias.abs().sum() == 0
+    assert abs(float(t["ipa_0"].head_weights[0]) - 0.541324854612918) < 1e-6
+
+
+def test_time_frequencies_bitwise():
+    from pepflowww_b200.utils_time import get_time_embedding
+    t = torch.tensor([0.01, 0.5, 1.0])
+    assert torch.equal(get_time_embedding(t, 128, 2056), orc.time_embedding(t))
