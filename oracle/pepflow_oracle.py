@@ -313,7 +313,7 @@ def mlp3(sd, p, x):
 
 
 def ga_encoder_forward(sd, t, rotmats_t, trans_t, angles_t, seqs_t, node_embed, edge_embed,
-                       generate_mask, res_mask, p="ga_encoder.", num_blocks=6, return_node=False):
+                       generate_mask, res_mask, p="ga_encoder.", num_blocks=6, return_node=False, trace=None):
     """GAEncoder.forward, models_con/ga.py:87-127.  t [B,1]; masks are long/float [B,L]."""
     B, L = seqs_t.shape
     m = res_mask.float()
@@ -326,19 +326,27 @@ def ga_encoder_forward(sd, t, rotmats_t, trans_t, angles_t, seqs_t, node_embed, 
     fr = Frames(trans_t, rot=rotmats_t.float())                                                    # :96
     z = edge_embed
     valid = m > 0
+    rec = (lambda name, x: trace.append((name, x.clone()))) if trace is not None else (lambda name, x: None)
+    rec("mix", s)
     for b in range(num_blocks):
         tp = f"{p}trunk."
         ipa = ipa_forward(sd, f"{tp}ipa_{b}.", s, z, fr, m) * m[..., None]                          # :98-103
+        rec(f"ipa_{b}", ipa)
         s = layer_norm(s + ipa, sd[f"{tp}ipa_ln_{b}.weight"], sd[f"{tp}ipa_ln_{b}.bias"])           # :104
         y = s
         for l in range(2):                                                                          # :105-106
             y = transformer_encoder_layer(sd, f"{tp}seq_tfmr_{b}.layers.{l}.", y, valid)
+        rec(f"tfmr_{b}", y)
         s = s + linear(y, sd[f"{tp}post_tfmr_{b}.weight"], sd[f"{tp}post_tfmr_{b}.bias"])           # :107
         s = node_transition(sd, f"{tp}node_transition_{b}.", s) * m[..., None]                      # :108-109
+        rec(f"node_{b}", s)
         upd = linear(s * m[..., None], sd[f"{tp}bb_update_{b}.linear.weight"], sd[f"{tp}bb_update_{b}.linear.bias"])
         fr = rigid_compose_q_update(fr, upd, m[..., None])                                          # :112-113
+        rec(f"rot_{b}", fr.rot_mats())
+        rec(f"trans_{b}", fr.trans)
         if b < num_blocks - 1:                                                                      # :115-118
             z = edge_transition(sd, f"{tp}edge_transition_{b}.", s, z) * em[..., None]
+            rec(f"z_{b}", z)
     pred_trans = fr.trans
     pred_rot = fr.rot_mats()
     logits = mlp3(sd, p + "seq_net.", s)                                                           # :123

@@ -5,14 +5,13 @@
 //
 // 93.7 % of the denoiser's FLOPs (SURVEY.md finding 4).  Two sm_100a variants ("edge_impl"):
 //   0: fp32 CUDA-core kernel that follows the formula literally (x materialised in shared memory).
-//   1: 3xBF16 split-precision tensor-core kernel (mma.sync m16n8k16, fp32 accumulate).  The per-residue
+//   1: 3xFP16 split-precision tensor-core kernel (mma.sync m16n8k16, fp32 accumulate).  The per-residue
 //      parts of W1 x and W_f x are hoisted out of the pair loop (P_i + Q_j, U_i + V_j; verified 2.7e-6 in
 //      SURVEY.md App. F), the MLP chain stays in registers (accumulator fragments are re-used as the next
 //      GEMM's A fragments), W2 is resident in shared memory and W1z/W_f stream through a cp.async ring.
 //      z is read once and written once (in place allowed).
-#include <cuda_bf16.h>
-
 #include "pf_common.cuh"
+#include "pf_split.cuh"
 
 namespace pf {
 
@@ -127,7 +126,7 @@ __global__ void __launch_bounds__(256) edge_transition_v0_kernel(EdgeArgs a) {
 }
 
 // =================================================================================================
-// variant 1: 3xBF16 tensor cores
+// variant 1: 3xFP16 tensor cores
 // =================================================================================================
 // Packed weight fragment layout: for k-step ks (16 k), n-tile nt (8 n), lane = g*4+t:
 //   16 bytes = { hi(k=2t,2t+1), hi(k=2t+8,2t+9), lo(2t,2t+1), lo(2t+8,2t+9) } of row n = 8 nt + g
@@ -144,25 +143,6 @@ constexpr int E1_STAGES_PER_TILE = 10;
 constexpr int E1_STREAM_BYTES = 4 * E1_SLAB_WIDE + 12 * E1_SLAB_OUT + 4 * E1_SLAB_OUT;  // 114688
 constexpr int E1_ROWS = 128;
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);  // .x = first (lower address / lower k)
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// split a pair of fp32 into packed bf16 hi and packed bf16 lo (residual)
-__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-  __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
-  hi = *reinterpret_cast<uint32_t*>(&hv);
-  lo = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
-}
-
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
@@ -171,7 +151,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Repack kernel: fp32 weights -> packed bf16 hi/lo fragments.
+// Repack kernel: fp32 weights -> packed fp16 hi/lo fragments.
 //   w2pack  : W2  [192 n][192 k]            -> [12 ks][24 nt][32][16 B]
 //   stream  : W1z = W1[:, 0:64]  (4 ks x 24 nt) | Wf [64 n][192 k] (12 ks x 8 nt) | Wfz = Wf[:, 0:64] (4 ks x 8 nt)
 __global__ void edge_pack_weights_kernel(const float* __restrict__ w1, const float* __restrict__ w2,

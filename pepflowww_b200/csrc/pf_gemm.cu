@@ -3,12 +3,11 @@
 //
 // Two sm_100a variants behind pf_linear (option "gemm_impl"):
 //   0: fp32 CUDA-core SGEMM (64x64x16 tiles, 4x4 register micro-tiles, register-prefetch double buffer)
-//   1: 3xBF16 split-precision tensor-core GEMM (mma.sync m16n8k16, fp32 accumulate): each fp32
-//      operand is split into bf16 hi + bf16 lo and the product is hi*hi + lo*hi + hi*lo, which keeps
-//      ~16 mantissa bits - single-pass TF32/BF16 fails the 1e-4 parity bar (SURVEY.md finding 5).
-#include <cuda_bf16.h>
-
+//   1: 3xFP16 split-precision tensor-core GEMM (mma.sync m16n8k16, fp32 accumulate): each fp32
+//      operand is split into fp16 hi + fp16 lo and the product is hi*hi + lo*hi + hi*lo, which keeps
+//      ~22 significand bits - single-pass TF32/BF16 fails the 1e-4 parity bar (SURVEY.md finding 5).
 #include "pf_common.cuh"
+#include "pf_split.cuh"
 
 namespace pf {
 
@@ -104,31 +103,19 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3xBF16 tensor-core GEMM (mma.sync.m16n8k16).  CTA tile 128(M) x 64(N), BK = 32, 8 warps, each warp
-// 16 rows x 64 cols (8 n-tiles).  Operands are split to bf16 hi/lo while they are staged into smem.
+// 3xFP16 tensor-core GEMM (mma.sync.m16n8k16).  CTA tile 128(M) x 64(N), BK = 32, 8 warps, each warp
+// 16 rows x 64 cols (8 n-tiles).  Operands are split to fp16 hi/lo while they are staged into smem.
 // ------------------------------------------------------------------------------------------------
-constexpr int TM = 128, TN = 64, TK = 32, SKP = TK + 8;  // smem row = 40 bf16 = 80 B (16 B-aligned, ldmatrix conflict-free)
-
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-
-__device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, const uint32_t* b) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
+constexpr int TM = 128, TN = 64, TK = 32, SKP = TK + 8;  // smem row = 40 halves = 80 B (16 B-aligned, ldmatrix conflict-free)
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) bf16x3_gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ W,
+__global__ void __launch_bounds__(256) f16x3_gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                                              const float* __restrict__ bias,
                                                              const float* __restrict__ residual,
                                                              const float* __restrict__ rowmask,
                                                              float* __restrict__ Y, int M, int K, int N, int ldw, int act) {
-  __shared__ __align__(16) __nv_bfloat16 sAh[TM][SKP], sAl[TM][SKP];
-  __shared__ __align__(16) __nv_bfloat16 sWh[TN][SKP], sWl[TN][SKP];
+  __shared__ __align__(16) __half sAh[TM][SKP], sAl[TM][SKP];
+  __shared__ __align__(16) __half sWh[TN][SKP], sWl[TN][SKP];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
@@ -162,7 +149,7 @@ __global__ void __launch_bounds__(256) bf16x3_gemm_tn_kernel(const float* __rest
         }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) split_bf16(v[e], sAh[r][kq + e], sAl[r][kq + e]);
+      for (int e = 0; e < 4; ++e) split_one(v[e], sAh[r][kq + e], sAl[r][kq + e]);
     }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -183,7 +170,7 @@ __global__ void __launch_bounds__(256) bf16x3_gemm_tn_kernel(const float* __rest
         }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) split_bf16(v[e], sWh[r][kq + e], sWl[r][kq + e]);
+      for (int e = 0; e < 4; ++e) split_one(v[e], sWh[r][kq + e], sWl[r][kq + e]);
     }
     __syncthreads();
 #pragma unroll
@@ -206,9 +193,9 @@ __global__ void __launch_bounds__(256) bf16x3_gemm_tn_kernel(const float* __rest
         bh[1] = *reinterpret_cast<const uint32_t*>(&sWh[nr][ks + 2 * t + 8]);
         bl[0] = *reinterpret_cast<const uint32_t*>(&sWl[nr][ks + 2 * t]);
         bl[1] = *reinterpret_cast<const uint32_t*>(&sWl[nr][ks + 2 * t + 8]);
-        mma_bf16_16816(acc[nt], al, bh);   // small terms first
-        mma_bf16_16816(acc[nt], ah, bl);
-        mma_bf16_16816(acc[nt], ah, bh);
+        mma16816(acc[nt], al, bh[0], bh[1]);   // small terms first
+        mma16816(acc[nt], ah, bl[0], bl[1]);
+        mma16816(acc[nt], ah, bh[0], bh[1]);
       }
     }
     __syncthreads();
@@ -241,8 +228,8 @@ int launch_linear_full(const float* x, const float* w, int ldw, const float* bia
   const bool vec = (K % 4 == 0) && (ldw % 4 == 0) && aligned16(x) && aligned16(w);
   if (opt_gemm_impl() == 1) {
     dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
-    if (vec) bf16x3_gemm_tn_kernel<true><<<grid, 256, 0, st>>>(x, w, bias, residual, rowmask, y, M, K, N, ldw, act);
-    else bf16x3_gemm_tn_kernel<false><<<grid, 256, 0, st>>>(x, w, bias, residual, rowmask, y, M, K, N, ldw, act);
+    if (vec) f16x3_gemm_tn_kernel<true><<<grid, 256, 0, st>>>(x, w, bias, residual, rowmask, y, M, K, N, ldw, act);
+    else f16x3_gemm_tn_kernel<false><<<grid, 256, 0, st>>>(x, w, bias, residual, rowmask, y, M, K, N, ldw, act);
   } else {
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     if (vec) sgemm_tn_kernel<true><<<grid, 256, 0, st>>>(x, w, bias, residual, rowmask, y, M, K, N, ldw, act);

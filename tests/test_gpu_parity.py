@@ -106,20 +106,28 @@ def test_manifold_maps_golden(dev):
         so3_utils.geodesic_t(g["t"], g["target"][:5], g["base"])
 
 
-def test_manifold_roundtrip_large(dev):
-    """Size-independent properties at bench scale: Exp(Log(R)) = R, geodesic(0)=base, geodesic(1)=target."""
+def test_manifold_maps_bench_scale(dev):
+    """cfg4 scale (64 x 271 frames): Log / geodesic against the oracle on uniformly random rotations, and the
+    size-independent properties Exp(Log(R)) = R (away from the theta ~ pi window, where the reference's own
+    outer-product branch is only ~1e-2 accurate), geodesic(0) = base, geodesic(1) = target, orthogonality."""
     from pepflowww_b200 import ops, so3_utils
     n = 64 * 271
-    q = torch.randn(n, 4, device=dev)
-    R = ops.quat_to_rot(q / q.norm(dim=-1, keepdim=True))
-    q2 = torch.randn(n, 4, device=dev)
-    S = ops.quat_to_rot(q2 / q2.norm(dim=-1, keepdim=True))
-    assert float((so3_utils.rotvec_to_rotmat(so3_utils.rotmat_to_rotvec(R)) - R).abs().max()) < 5e-4
+    g = torch.Generator().manual_seed(1)
+    R = orc.quat_to_rot(torch.nn.functional.normalize(torch.randn(n, 4, generator=g), dim=-1))
+    S = orc.quat_to_rot(torch.nn.functional.normalize(torch.randn(n, 4, generator=g), dim=-1))
+    Rd, Sd = R.to(dev), S.to(dev)
+    w = so3_utils.rotmat_to_rotvec(Rd)
+    assert rel_err(w.cpu(), orc.so3_log(R)) < 1e-4
+    t = torch.full((1,), 0.3)
+    assert rel_err(so3_utils.geodesic_t(t.to(dev), Sd, Rd).cpu(), orc.geodesic_t(t, S, R)) < 1e-4
+    ok = w.norm(dim=-1) < 3.0
+    assert float((so3_utils.rotvec_to_rotmat(w) - Rd)[ok].abs().max()) < 1e-5
     one, zero = torch.ones(1, device=dev), torch.zeros(1, device=dev)
-    assert float((so3_utils.geodesic_t(zero, S, R) - R).abs().max()) < 1e-5
-    assert float((so3_utils.geodesic_t(one, S, R) - S).abs().max()) < 5e-4
-    RtR = torch.einsum("nji,njk->nik", so3_utils.geodesic_t(one * 0.3, S, R), so3_utils.geodesic_t(one * 0.3, S, R))
-    assert float((RtR - torch.eye(3, device=dev)).abs().max()) < 1e-5
+    assert float((so3_utils.geodesic_t(zero, Sd, Rd) - Rd).abs().max()) < 1e-5
+    rel_angle = so3_utils.calc_rot_vf(Rd, Sd).norm(dim=-1) < 3.0
+    assert float((so3_utils.geodesic_t(one, Sd, Rd) - Sd)[rel_angle].abs().max()) < 1e-5
+    G = so3_utils.geodesic_t(one * 0.3, Sd, Rd)
+    assert float((torch.einsum("nji,njk->nik", G, G) - torch.eye(3, device=dev))[rel_angle].abs().max()) < 1e-5
 
 
 @pytest.mark.parametrize("tag", ["ga_encoder_a", "ga_encoder_b"])
