@@ -32,7 +32,24 @@ def main():
     sd = deterministic_state_dict(model.state_dict(), 114514)
     model.load_state_dict(sd)
     model = model.to(dev)
-    g = load_golden(sys.argv[3] if len(sys.argv) > 3 else "ga_encoder_a")
+    tag = sys.argv[3] if len(sys.argv) > 3 else "ga_encoder_a"
+    if tag.startswith("synth"):   # synth:<pocket>:<peptide>  - embedder outputs of a synthetic batch, like smoke()
+        from pepflowww_b200.pep_dataloader import synthetic_batch
+        _, lr, lp = tag.split(":")
+        batch = synthetic_batch(2, int(lr), int(lp), seed=5)
+        enc = orc.encode(sd, batch)
+        B, L = batch["aa"].shape
+        gen = torch.Generator().manual_seed(0)
+        gm = batch["generate_mask"]
+        R0 = orc.quat_to_rot(torch.nn.functional.normalize(torch.randn(B, L, 4, generator=gen), dim=-1))
+        g = {"t": torch.full((B, 1), 0.01), "rotmats_t": torch.where(gm[..., None, None], R0, enc["rotmats_1"]),
+             "trans_t": torch.where(gm[..., None], torch.randn(B, L, 3, generator=gen), enc["trans_1"]),
+             "angles_t": torch.where(gm[..., None], torch.rand(B, L, 5, generator=gen) * 2 * math.pi, enc["angles_1"]),
+             "seqs_t": torch.where(gm, torch.randint(0, 20, (B, L), generator=gen), enc["seqs_1"]),
+             "node_embed": enc["node_embed"], "edge_embed": enc["edge_embed"], "generate_mask": gm.long(),
+             "res_mask": batch["res_mask"].long()}
+    else:
+        g = load_golden(tag)
     keys = ("t", "rotmats_t", "trans_t", "angles_t", "seqs_t", "node_embed", "edge_embed", "generate_mask", "res_mask")
     trace = []
     ref = orc.ga_encoder_forward(sd, *[g[k] for k in keys], trace=trace)

@@ -345,18 +345,48 @@ def test_sample_loop_golden(dev, model, impl):
     assert set(traj[0]) == {"rotmats", "trans", "angles", "seqs", "seqs_simplex", "rotmats_1", "trans_1", "angles_1", "seqs_1"}
     for k, v in before.items():
         assert torch.equal(batch[k], v)          # sample must not mutate the batch
-    for i, d in enumerate(traj):
-        assert torch.equal(d["seqs"], s[f"step{i}_seqs"]), i
-        assert rel_err(d["rotmats"], s[f"step{i}_rotmats"]) < 5e-4, i     # free-running over i steps
-        assert rel_err(d["trans"], s[f"step{i}_trans"]) < 5e-4, i
-        assert circ_err(d["angles"], s[f"step{i}_angles"]) < 2e-3, i
-        assert torch.equal(d["seqs_simplex"], s[f"step{i}_seqs_simplex"]), i
-    # step 0 is a single teacher-forced denoiser call: the 1e-4 bar applies
+    # step 0 is a single denoiser call from the recorded noise: the 1e-4 bar applies
+    assert torch.equal(traj[0]["seqs"], s["step0_seqs"])
     assert rel_err(traj[0]["rotmats"], s["step0_rotmats"]) < TOL
     assert rel_err(traj[0]["trans"], s["step0_trans"]) < TOL
+    assert circ_err(traj[0]["angles"], s["step0_angles"]) < TOL * 2 * math.pi
     # context (pocket) rows are returned untouched
     ctx = ~g["generate_mask"]
     assert torch.equal(traj[-1]["trans"][ctx], g["trans_1"][ctx])
+
+    # Teacher-forced per step (SURVEY.md finding 8): the SO(3) log near theta ~ pi makes the free-running loop
+    # sensitive to 1e-6 perturbations, so every iteration restarts from the reference's own state, rebuilt on the
+    # CPU from the golden clean predictions with the (pinned) oracle Euler update.
+    from pepflowww_b200.constants import torsions_mask
+    gen = g["generate_mask"]
+    gt = (g["rotmats_1"], g["trans_1"], g["angles_1"], g["seqs_1"])
+    state = (s["rotmats_0"], s["trans_0"], s["angles_0"], s["seqs_0"], s["seqs_0_simplex"])
+    noise0 = (s["trans_0"], s["seqs_0_simplex"])
+    ts = torch.linspace(1e-2, 1.0, 4)
+    smp = model.sampler_init(batch, num_steps=4, noise=noise, uniforms=uni)
+    for n in range(4):
+        smp.rot_t.copy_(state[0]); smp.tr_t.copy_(state[1]); smp.ang_t.copy_(state[2])
+        smp.seq_t.copy_(state[3]); smp.sx_t.copy_(state[4])
+        smp.step(n)
+        got = {k: v[n].cpu() for k, v in smp.traj.items()}
+        assert torch.equal(got["seqs"], s[f"step{n}_seqs"]), n
+        assert rel_err(got["rotmats"], s[f"step{n}_rotmats"]) < TOL, n
+        assert rel_err(got["trans"], s[f"step{n}_trans"]) < TOL, n
+        assert circ_err(got["angles"], s[f"step{n}_angles"]) < TOL * 2 * math.pi, n
+        assert torch.equal(got["seqs_simplex"], s[f"step{n}_seqs_simplex"]), n
+        if n == 3:
+            break
+        clean = (s[f"step{n}_rotmats"], s[f"step{n}_trans"], s[f"step{n}_angles"], s[f"step{n}_seqs"])
+        w = orc.calc_rot_vf(state[0], clean[0]).norm(dim=-1)
+        state = orc.euler_update(state, clean, gt, noise0, gen, ts[n + 1] - ts[n], uni[n, 1], torsions_mask)
+        # the GPU Euler update started from (reference state, GPU clean prediction): same residue types, and the
+        # manifold state within tolerance wherever the rotation step is well conditioned
+        assert torch.equal(smp.seq_t.cpu(), state[3]), n
+        assert rel_err(smp.tr_t.cpu(), state[1]) < TOL, n
+        assert rel_err(smp.sx_t.cpu(), state[4]) < 1e-6, n
+        assert circ_err(smp.ang_t.cpu(), state[2]) < TOL * 2 * math.pi, n
+        well = (w < 3.0) | ~gen
+        assert rel_err(smp.rot_t.cpu()[well], state[0][well]) < 5 * TOL, n
 
 
 def test_sample_free_running_flags_and_shapes(dev, model):
