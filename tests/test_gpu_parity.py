@@ -340,7 +340,10 @@ def test_sample_loop_golden(dev, model, impl):
     B, L = g["aa"].shape
     uni = s["uniforms"][1:].reshape(4, 2, B, L)
     before = {k: v.clone() for k, v in batch.items()}
-    traj = model.sample(batch, num_steps=4, noise=noise, uniforms=uni)
+    # encoder outputs (once-per-sample embedders, outside the hot path) are the reference's own, so the
+    # comparison isolates the per-step path; test_embedders_on_gpu covers the embedders separately
+    enc = tuple(g[k].to(dev) for k in ("rotmats_1", "trans_1", "angles_1", "seqs_1", "node_embed", "edge_embed"))
+    traj = model.sample(batch, num_steps=4, noise=noise, uniforms=uni, encoded=enc)
     assert len(traj) == 4 and all(not v.is_cuda for v in traj[0].values())
     assert set(traj[0]) == {"rotmats", "trans", "angles", "seqs", "seqs_simplex", "rotmats_1", "trans_1", "angles_1", "seqs_1"}
     for k, v in before.items():
@@ -363,7 +366,7 @@ def test_sample_loop_golden(dev, model, impl):
     state = (s["rotmats_0"], s["trans_0"], s["angles_0"], s["seqs_0"], s["seqs_0_simplex"])
     noise0 = (s["trans_0"], s["seqs_0_simplex"])
     ts = torch.linspace(1e-2, 1.0, 4)
-    smp = model.sampler_init(batch, num_steps=4, noise=noise, uniforms=uni)
+    smp = model.sampler_init(batch, num_steps=4, noise=noise, uniforms=uni, encoded=enc)
     for n in range(4):
         smp.rot_t.copy_(state[0]); smp.tr_t.copy_(state[1]); smp.ang_t.copy_(state[2])
         smp.seq_t.copy_(state[3]); smp.sx_t.copy_(state[4])
@@ -387,6 +390,20 @@ def test_sample_loop_golden(dev, model, impl):
         assert circ_err(smp.ang_t.cpu(), state[2]) < TOL * 2 * math.pi, n
         well = (w < 3.0) | ~gen
         assert rel_err(smp.rot_t.cpu()[well], state[0][well]) < 5 * TOL, n
+
+
+def test_embedders_on_gpu(dev, model):
+    """The PyTorch embedders (once per sample, SURVEY section 8f 'next' rows) on the GPU against the
+    reference's CPU outputs.  Looser bound: acos() in the dihedral features amplifies fp32 differences."""
+    g = load_golden("encode")
+    batch = {k: g[k].to(dev) for k in ("aa", "pos_heavyatom", "mask_heavyatom", "res_nb", "chain_nb", "generate_mask",
+                                       "res_mask", "torsion_angle", "torsion_angle_mask")}
+    with torch.no_grad():
+        enc = model.encode(batch)
+    assert rel_err(enc[0].cpu(), g["rotmats_1"]) < 1e-5
+    assert rel_err(enc[4].cpu(), g["node_embed"]) < 2e-3
+    assert rel_err(enc[5].cpu(), g["edge_embed"]) < 2e-3
+    print("embedder gpu-vs-cpu: node %.2e edge %.2e" % (rel_err(enc[4].cpu(), g["node_embed"]), rel_err(enc[5].cpu(), g["edge_embed"])))
 
 
 def test_sample_free_running_flags_and_shapes(dev, model):
