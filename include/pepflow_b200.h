@@ -86,9 +86,11 @@ int pf_ipa_points(const float* proj, const float* rot, const float* trans, float
  * o, o_pt (back in the local frame, plus norms) and o_pair; writes feats[B*L,1536] in the
  * reference's concat order (ipa_pytorch.py:475).  z [B,L,L,64] is read once.
  * head_w = softplus(head_weights)*sqrt(1/108) precomputed by the caller ([8]). */
+size_t pf_ipa_attention_workspace_bytes(int B, int L);   /* fp16 hi/lo operand fragments of the tensor-core variant */
 int pf_ipa_attention(const float* proj, const float* pts, const float* z, const float* w_b, const float* b_b,
                      const float* w_dz, const float* b_dz, const float* head_w, const float* rot,
-                     const float* trans, const float* mask, float* feats, int B, int L, void* stream);
+                     const float* trans, const float* mask, float* feats, void* workspace, size_t workspace_bytes,
+                     int B, int L, void* stream);
 
 /* ---- K5: sequence transformer attention core (torch.nn.TransformerEncoderLayer, ga.py:53-62) - */
 /* qkv[B*L,384] (in_proj output) -> ctx[B*L,128]; 4 heads x 32, key-padding mask (mask==0 keys skipped). */

@@ -33,7 +33,8 @@ SIGNATURES = {
     "pf_add_layernorm": (_i, [_p] * 6 + [_i] * 2 + [_p]),
     "pf_mix_features": (_i, [_p] * 8 + [_i] * 2 + [_p]),
     "pf_ipa_points": (_i, [_p] * 4 + [_i] * 2 + [_p]),
-    "pf_ipa_attention": (_i, [_p] * 12 + [_i] * 2 + [_p]),
+    "pf_ipa_attention_workspace_bytes": (_sz, [_i, _i]),
+    "pf_ipa_attention": (_i, [_p] * 13 + [_sz] + [_i] * 2 + [_p]),
     "pf_seq_attention": (_i, [_p] * 3 + [_i] * 2 + [_p]),
     "pf_rigid_update": (_i, [_p] * 8 + [_i] + [_p]),
     "pf_edge_transition_workspace_bytes": (_sz, [_i, _i]),

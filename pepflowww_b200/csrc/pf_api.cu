@@ -12,7 +12,7 @@ namespace pf {
 
 static std::atomic<int64_t> g_launches{0};
 static int g_num_sms = 148;
-static std::atomic<int> g_edge_impl{1}, g_gemm_impl{1}, g_ipa_impl{0};
+static std::atomic<int> g_edge_impl{1}, g_gemm_impl{1}, g_ipa_impl{1};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -53,7 +53,8 @@ static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 struct GaWorkspace {
   float *xmix, *s, *ta, *tb, *ya, *yb, *proj, *pts, *feats, *qkv, *ctx, *quat, *rot, *trans, *upd, *ang_raw, *zbuf;
   void* edge_ws;
-  size_t edge_ws_bytes, total;
+  void* ipa_ws;
+  size_t edge_ws_bytes, ipa_ws_bytes, total;
 };
 
 static GaWorkspace carve(void* base, int B, int L) {
@@ -85,6 +86,8 @@ static GaWorkspace carve(void* base, int B, int L) {
   w.zbuf = take(M * L * CZ * 4);
   w.edge_ws_bytes = edge_workspace_bytes(B, L);
   w.edge_ws = take(w.edge_ws_bytes);
+  w.ipa_ws_bytes = ipa_workspace_bytes(B, L);
+  w.ipa_ws = take(w.ipa_ws_bytes);
   w.total = off;
   return w;
 }
@@ -122,6 +125,7 @@ int pf_init(int device) {
   pf::g_num_sms = sms;
   pf::node_kernels_init();
   pf::ipa_kernels_init();
+  pf::ipa_tc_kernels_init();
   pf::edge_kernels_init();
   e = cudaGetLastError();
   return e == cudaSuccess ? PF_OK : static_cast<int>(e);
@@ -138,7 +142,7 @@ int pf_set_option(const char* name, int value) {
   if (!name) return PF_ERR_NULL_POINTER;
   if (!std::strcmp(name, "edge_impl") && (value == 0 || value == 1)) { pf::g_edge_impl = value; return PF_OK; }
   if (!std::strcmp(name, "gemm_impl") && (value == 0 || value == 1)) { pf::g_gemm_impl = value; return PF_OK; }
-  if (!std::strcmp(name, "ipa_impl") && (value == 0)) { pf::g_ipa_impl = value; return PF_OK; }
+  if (!std::strcmp(name, "ipa_impl") && (value == 0 || value == 1)) { pf::g_ipa_impl = value; return PF_OK; }
   return PF_ERR_BAD_OPTION;
 }
 
@@ -226,7 +230,7 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
     PF_TRY(launch_ipa_points(ws.proj, rot, trans, ws.pts, M, st));
     IpaArgs ia{ws.proj, ws.pts, z, W[PF_B_LINB_W], W[PF_B_LINB_B], W[PF_B_DOWNZ_W], W[PF_B_DOWNZ_B], W[PF_B_HEAD_W],
                rot, trans, res_mask, ws.feats, B, L};
-    PF_TRY(launch_ipa_attention(ia, st));
+    PF_TRY(launch_ipa_attention(ia, ws.ipa_ws, ws.ipa_ws_bytes, st));
     PF_TRY(launch_linear(ws.feats, W[PF_B_OUT_W], W[PF_B_OUT_B], nullptr, res_mask, ws.ta, M, NFEAT, 128, 0, st));
     PF_TRY(launch_add_layernorm(ws.s, ws.ta, W[PF_B_IPA_LN_G], W[PF_B_IPA_LN_B], nullptr, ws.s, M, 128, st));
     // sequence transformer, 2 post-norm layers (ga.py:105-106)

@@ -108,7 +108,10 @@ int launch_rigid_update(const float* quat_in, const float* rot_in, const float* 
 int launch_ipa_points(const float* proj, const float* rot, const float* trans, float* pts, int rows, cudaStream_t st);
 int launch_mod_2pi(const float* x, float* y, int n, cudaStream_t st);
 int launch_quat_to_rot(const float* quat, float* rot, int n, cudaStream_t st);
-int launch_ipa_attention(const IpaArgs& a, cudaStream_t st);
+size_t ipa_workspace_bytes(int B, int L);
+int launch_ipa_attention(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_ipa_attention_v1(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
+void ipa_tc_kernels_init();
 size_t edge_workspace_bytes(int B, int L);
 int launch_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,
                            const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,

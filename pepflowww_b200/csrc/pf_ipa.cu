@@ -204,8 +204,9 @@ size_t ipa_v0_smem(int L) {
   return (size_t)(TI * H * C + TI * H * PQ * 3 + H * CZ + H * TI * 100 + (size_t)H * TI * Lp) * sizeof(float);
 }
 
-int launch_ipa_attention(const IpaArgs& a, cudaStream_t st) {
+int launch_ipa_attention(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (a.B == 0 || a.L == 0) return PF_OK;
+  if (opt_ipa_impl() == 1) return launch_ipa_attention_v1(a, workspace, workspace_bytes, st);
   const size_t smem = ipa_v0_smem(a.L);
   if (smem > 227 * 1024) return PF_ERR_BAD_SHAPE;  // L <= ~1600
   dim3 grid((a.L + TI - 1) / TI, a.B);
@@ -222,14 +223,16 @@ void ipa_kernels_init() {
 
 }  // namespace pf
 
+extern "C" size_t pf_ipa_attention_workspace_bytes(int B, int L) { return pf::ipa_workspace_bytes(B, L); }
+
 extern "C" int pf_ipa_attention(const float* proj, const float* pts, const float* z, const float* w_b,
                                 const float* b_b, const float* w_dz, const float* b_dz, const float* head_w,
-                                const float* rot, const float* trans, const float* mask, float* feats, int B,
-                                int L, void* stream) {
+                                const float* rot, const float* trans, const float* mask, float* feats,
+                                void* workspace, size_t workspace_bytes, int B, int L, void* stream) {
   PF_REQUIRE(proj && pts && z && w_b && b_b && w_dz && b_dz && head_w && rot && trans && mask && feats,
              PF_ERR_NULL_POINTER);
   PF_REQUIRE(B >= 0 && L >= 0, PF_ERR_BAD_SHAPE);
   PF_REQUIRE(pf::aligned16(proj) && pf::aligned16(z) && pf::aligned16(feats) && pf::aligned16(pts), PF_ERR_MISALIGNED);
   pf::IpaArgs a{proj, pts, z, w_b, b_b, w_dz, b_dz, head_w, rot, trans, mask, feats, B, L};
-  return pf::launch_ipa_attention(a, pf::as_stream(stream));
+  return pf::launch_ipa_attention(a, workspace, workspace_bytes, pf::as_stream(stream));
 }

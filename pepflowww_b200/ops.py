@@ -68,9 +68,11 @@ def ipa_attention(proj, pts, z, w_b, b_b, w_dz, b_dz, head_w, rot, trans, mask):
     lib = _lib.lib_for(proj.device)
     B, L = proj.shape[:2]
     feats = torch.empty(B, L, 1536, device=proj.device, dtype=F32)
+    nbytes = lib.pf_ipa_attention_workspace_bytes(B, L)
+    ws = torch.empty(nbytes, device=proj.device, dtype=U8)
     check(lib.pf_ipa_attention(ptr(_c(proj)), ptr(_c(pts)), ptr(_c(z)), ptr(_c(w_b)), ptr(_c(b_b)), ptr(_c(w_dz)),
                                ptr(_c(b_dz)), ptr(_c(head_w)), ptr(_c(rot).reshape(B, L, 9)), ptr(_c(trans)),
-                               ptr(_c(mask)), ptr(feats), B, L, stream()))
+                               ptr(_c(mask)), ptr(feats), ptr(ws, U8), nbytes, B, L, stream()))
     return feats
 
 

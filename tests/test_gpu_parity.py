@@ -33,15 +33,18 @@ def model(dev, state_dict):
     return m.to(dev)
 
 
-@pytest.fixture(params=[(0, 0), (1, 1), (1, 0), (0, 1)], ids=["fp32", "tc", "edge_tc", "gemm_tc"])
+@pytest.fixture(params=[(0, 0, 0), (1, 1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1)],
+                ids=["fp32", "tc", "edge_tc", "gemm_tc", "ipa_tc"])
 def impl(request):
     from pepflowww_b200 import _lib
-    edge, gemm = request.param
+    edge, gemm, ipa = request.param
     _lib.set_option("edge_impl", edge)
     _lib.set_option("gemm_impl", gemm)
+    _lib.set_option("ipa_impl", ipa)
     yield request.param
     _lib.set_option("edge_impl", 1)
     _lib.set_option("gemm_impl", 1)
+    _lib.set_option("ipa_impl", 1)
 
 
 def cu(g, dev, keys):
