@@ -142,6 +142,24 @@ constexpr int E1_NSTAGE = 3;
 constexpr int E1_STAGES_PER_TILE = 10;
 constexpr int E1_STREAM_BYTES = 4 * E1_SLAB_WIDE + 12 * E1_SLAB_OUT + 4 * E1_SLAB_OUT;  // 114688
 constexpr int E1_ROWS = 128;
+constexpr int E1_G = 4;                              // n-tiles interleaved per MMA group
+
+// 3xFP16 product of one A fragment with G consecutive n-tiles of packed B fragments.  The three MMAs of an
+// n-tile form a dependent chain on its accumulator, so G independent chains are interleaved to cover the
+// mma.sync latency (measured: strictly sequential chains ran at ~15 cycles per MMA per scheduler).
+template <int G, int NACC>
+__device__ __forceinline__ void mma3_group(float (&acc)[NACC][4], int nt0, const uint32_t (&ah)[4],
+                                           const uint32_t (&al)[4], const uint4* wp, int lane) {
+  uint4 w[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q) w[q] = wp[q * 32 + lane];
+#pragma unroll
+  for (int q = 0; q < G; ++q) mma16816(acc[nt0 + q], al, w[q].x, w[q].y);
+#pragma unroll
+  for (int q = 0; q < G; ++q) mma16816(acc[nt0 + q], ah, w[q].z, w[q].w);
+#pragma unroll
+  for (int q = 0; q < G; ++q) mma16816(acc[nt0 + q], ah, w[q].x, w[q].y);
+}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
@@ -282,12 +300,7 @@ __global__ void __launch_bounds__(256, 1) edge_transition_v1_kernel(Edge1Args a)
     for (int ks = 0; ks < E1_KS_Z; ++ks) {
       const uint4* wp = acquire();
 #pragma unroll
-      for (int nt = 0; nt < 24; ++nt) {
-        const uint4 w = wp[nt * 32 + lane];
-        mma16816(acc[nt], al[ks], w.x, w.y);
-        mma16816(acc[nt], ah[ks], w.z, w.w);
-        mma16816(acc[nt], ah[ks], w.x, w.y);
-      }
+      for (int nt = 0; nt < 24; nt += E1_G) mma3_group<E1_G>(acc, nt, ah[ks], al[ks], wp + nt * 32, lane);
     }
     // ---- h1 = relu(.) -> A fragments (C fragment of n-tiles 2ks, 2ks+1 == A fragment of k-step ks)
 #pragma unroll
@@ -307,12 +320,7 @@ __global__ void __launch_bounds__(256, 1) edge_transition_v1_kernel(Edge1Args a)
     for (int ks = 0; ks < E1_KS_H; ++ks) {
       const uint4* wp = sW2 + ks * (E1_NT_WIDE * 32);
 #pragma unroll
-      for (int nt = 0; nt < 24; ++nt) {
-        const uint4 w = wp[nt * 32 + lane];
-        mma16816(acc[nt], al[ks], w.x, w.y);
-        mma16816(acc[nt], ah[ks], w.z, w.w);
-        mma16816(acc[nt], ah[ks], w.x, w.y);
-      }
+      for (int nt = 0; nt < 24; nt += E1_G) mma3_group<E1_G>(acc, nt, ah[ks], al[ks], wp + nt * 32, lane);
     }
     // ---- h2 = relu(.) -> A fragments
 #pragma unroll
@@ -343,12 +351,8 @@ __global__ void __launch_bounds__(256, 1) edge_transition_v1_kernel(Edge1Args a)
       for (int k3 = 0; k3 < 3; ++k3) {
         const int ks = st * 3 + k3;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          const uint4 w = wp[(k3 * E1_NT_OUT + nt) * 32 + lane];
-          mma16816(y[nt], al[ks], w.x, w.y);
-          mma16816(y[nt], ah[ks], w.z, w.w);
-          mma16816(y[nt], ah[ks], w.x, w.y);
-        }
+        for (int nt = 0; nt < 8; nt += E1_G)
+          mma3_group<E1_G>(y, nt, ah[ks], al[ks], wp + (k3 * E1_NT_OUT + nt) * 32, lane);
       }
     }
     // z again (registers were recycled): A fragments for the residual path
@@ -371,12 +375,8 @@ __global__ void __launch_bounds__(256, 1) edge_transition_v1_kernel(Edge1Args a)
       for (int k2 = 0; k2 < 2; ++k2) {
         const int ks = st * 2 + k2;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          const uint4 w = wp[(k2 * E1_NT_OUT + nt) * 32 + lane];
-          mma16816(y[nt], al[ks], w.x, w.y);
-          mma16816(y[nt], ah[ks], w.z, w.w);
-          mma16816(y[nt], ah[ks], w.x, w.y);
-        }
+        for (int nt = 0; nt < 8; nt += E1_G)
+          mma3_group<E1_G>(y, nt, ah[ks], al[ks], wp + (k2 * E1_NT_OUT + nt) * 32, lane);
       }
     }
     // ---- LayerNorm over 64 outputs: a row lives in the 4 lanes of a quad (16 values each)

@@ -194,16 +194,22 @@ __global__ void __launch_bounds__(256) f16x3_gemm_tn_kernel(const float* __restr
       al[2] = *reinterpret_cast<const uint32_t*>(&sAl[r0][ks + 2 * t + 8]);
       al[3] = *reinterpret_cast<const uint32_t*>(&sAl[r0 + 8][ks + 2 * t + 8]);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        uint32_t bh[2], bl[2];
-        const int nr = nt * 8 + g;
-        bh[0] = *reinterpret_cast<const uint32_t*>(&sWh[nr][ks + 2 * t]);
-        bh[1] = *reinterpret_cast<const uint32_t*>(&sWh[nr][ks + 2 * t + 8]);
-        bl[0] = *reinterpret_cast<const uint32_t*>(&sWl[nr][ks + 2 * t]);
-        bl[1] = *reinterpret_cast<const uint32_t*>(&sWl[nr][ks + 2 * t + 8]);
-        mma16816(chunk[nt], al, bh[0], bh[1]);   // small terms first
-        mma16816(chunk[nt], ah, bl[0], bl[1]);
-        mma16816(chunk[nt], ah, bh[0], bh[1]);
+      for (int n0 = 0; n0 < 8; n0 += 4) {              // 4 independent accumulator chains per group
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int nr = (n0 + q) * 8 + g;
+          bh[q][0] = *reinterpret_cast<const uint32_t*>(&sWh[nr][ks + 2 * t]);
+          bh[q][1] = *reinterpret_cast<const uint32_t*>(&sWh[nr][ks + 2 * t + 8]);
+          bl[q][0] = *reinterpret_cast<const uint32_t*>(&sWl[nr][ks + 2 * t]);
+          bl[q][1] = *reinterpret_cast<const uint32_t*>(&sWl[nr][ks + 2 * t + 8]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mma16816(chunk[n0 + q], al, bh[q][0], bh[q][1]);   // small terms first
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mma16816(chunk[n0 + q], ah, bl[q][0], bl[q][1]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mma16816(chunk[n0 + q], ah, bh[q][0], bh[q][1]);
       }
     }
 #pragma unroll

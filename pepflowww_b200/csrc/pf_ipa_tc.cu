@@ -218,41 +218,58 @@ __global__ void __launch_bounds__(256, 1) ipa_attention_v1_kernel(Ipa1Args p) {
     const float* zt = zs + st * SM_Z_STAGE;
 
     // ================= phase 1 (pair-major): pair bias for rows 2w, 2w+1, all heads
+    {
+      float acc[2][2][4];                              // [m-tile][small terms | hi*hi]: 4 independent MMA chains
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const int i = 2 * warp + mt;                     // m-tile = one query row, 16 keys
-      const float* zr_lo = zt + (i * TKEY + g) * ZP;   // pair (i, j = g)
-      const float* zr_hi = zt + (i * TKEY + g + 8) * ZP;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { acc[mt][q][0] = acc[mt][q][1] = acc[mt][q][2] = acc[mt][q][3] = 0.f; }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const int c = ks * 16 + 2 * t;
-        const float2 x0 = *reinterpret_cast<const float2*>(zr_lo + c);
-        const float2 x1 = *reinterpret_cast<const float2*>(zr_hi + c);
-        const float2 x2 = *reinterpret_cast<const float2*>(zr_lo + c + 8);
-        const float2 x3 = *reinterpret_cast<const float2*>(zr_hi + c + 8);
-        uint32_t ah[4], al[4];
-        split_pair(x0.x, x0.y, ah[0], al[0]);
-        split_pair(x1.x, x1.y, ah[1], al[1]);
-        split_pair(x2.x, x2.y, ah[2], al[2]);
-        split_pair(x3.x, x3.y, ah[3], al[3]);
-        mma16816(acc, al, wbh[ks][0], wbh[ks][1]);
-        mma16816(acc, ah, wbl[ks][0], wbl[ks][1]);
-        mma16816(acc, ah, wbh[ks][0], wbh[ks][1]);
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {               // m-tile = one query row (i = 2w + mt), 16 keys
+          const int i = 2 * warp + mt;
+          const float* zr_lo = zt + (i * TKEY + g) * ZP;       // pair (i, j = g)
+          const float* zr_hi = zt + (i * TKEY + g + 8) * ZP;   // pair (i, j = g + 8)
+          const int c = ks * 16 + 2 * t;
+          const float2 x0 = *reinterpret_cast<const float2*>(zr_lo + c);
+          const float2 x1 = *reinterpret_cast<const float2*>(zr_hi + c);
+          const float2 x2 = *reinterpret_cast<const float2*>(zr_lo + c + 8);
+          const float2 x3 = *reinterpret_cast<const float2*>(zr_hi + c + 8);
+          split_pair(x0.x, x0.y, ah[mt][0], al[mt][0]);
+          split_pair(x1.x, x1.y, ah[mt][1], al[mt][1]);
+          split_pair(x2.x, x2.y, ah[mt][2], al[mt][2]);
+          split_pair(x3.x, x3.y, ah[mt][3], al[mt][3]);
+        }
+        mma16816(acc[0][0], al[0], wbh[ks][0], wbh[ks][1]);
+        mma16816(acc[1][0], al[1], wbh[ks][0], wbh[ks][1]);
+        mma16816(acc[0][1], ah[0], wbh[ks][0], wbh[ks][1]);
+        mma16816(acc[1][1], ah[1], wbh[ks][0], wbh[ks][1]);
+        mma16816(acc[0][0], ah[0], wbl[ks][0], wbl[ks][1]);
+        mma16816(acc[1][0], ah[1], wbl[ks][0], wbl[ks][1]);
       }
-      // C: (pair row g -> key j = g, head 2t,2t+1), (row g+8 -> key g+8)
-      sbias[((2 * t) * TQ + i) * BP + g] = acc[0];
-      sbias[((2 * t + 1) * TQ + i) * BP + g] = acc[1];
-      sbias[((2 * t) * TQ + i) * BP + g + 8] = acc[2];
-      sbias[((2 * t + 1) * TQ + i) * BP + g + 8] = acc[3];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int i = 2 * warp + mt;
+        // C: (pair row g -> key j = g, head 2t,2t+1), (row g+8 -> key g+8)
+        sbias[((2 * t) * TQ + i) * BP + g] = acc[mt][0][0] + acc[mt][1][0];
+        sbias[((2 * t + 1) * TQ + i) * BP + g] = acc[mt][0][1] + acc[mt][1][1];
+        sbias[((2 * t) * TQ + i) * BP + g + 8] = acc[mt][0][2] + acc[mt][1][2];
+        sbias[((2 * t + 1) * TQ + i) * BP + g + 8] = acc[mt][0][3] + acc[mt][1][3];
+      }
     }
     __syncthreads();                                   // (A) bias tile complete
 
     // ================= phase 2 (head-major): S = Q K^T for head h
     float S[2][4];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) { S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f; }
     {
+      float Sa[2][4], Sb[2][4];                        // [n-tile]: small terms / hi*hi -> 4 independent chains
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        Sa[nt][0] = Sa[nt][1] = Sa[nt][2] = Sa[nt][3] = 0.f;
+        Sb[nt][0] = Sb[nt][1] = Sb[nt][2] = Sb[nt][3] = 0.f;
+      }
       const uint4* kp = p.Kp + (((size_t)b * H + h) * p.JT + jt) * kp_tile_u4();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
@@ -260,13 +277,17 @@ __global__ void __launch_bounds__(256, 1) ipa_attention_v1_kernel(Ipa1Args p) {
         const uint4 k1 = kp[(ks * 2 + 1) * 32 + lane];
         const uint32_t ah[4] = {qh[ks].x, qh[ks].y, qh[ks].z, qh[ks].w};
         const uint32_t al[4] = {ql[ks].x, ql[ks].y, ql[ks].z, ql[ks].w};
-        mma16816(S[0], al, k0.x, k0.y);
-        mma16816(S[0], ah, k0.z, k0.w);
-        mma16816(S[0], ah, k0.x, k0.y);
-        mma16816(S[1], al, k1.x, k1.y);
-        mma16816(S[1], ah, k1.z, k1.w);
-        mma16816(S[1], ah, k1.x, k1.y);
+        mma16816(Sa[0], al, k0.x, k0.y);
+        mma16816(Sa[1], al, k1.x, k1.y);
+        mma16816(Sb[0], ah, k0.x, k0.y);
+        mma16816(Sb[1], ah, k1.x, k1.y);
+        mma16816(Sa[0], ah, k0.z, k0.w);
+        mma16816(Sa[1], ah, k1.z, k1.w);
       }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) S[nt][e] = Sa[nt][e] + Sb[nt][e];
     }
     // ================= phase 3: logits, online softmax
     {
@@ -346,11 +367,16 @@ __global__ void __launch_bounds__(256, 1) ipa_attention_v1_kernel(Ipa1Args p) {
       split_pair(S[1][2], S[1][3], ph[3], pl[3]);      // a3: row g+8
       const uint4* vp = p.Vp + (((size_t)b * H + h) * p.JT + jt) * vp_tile_u4();
 #pragma unroll
-      for (int n = 0; n < VNT; ++n) {
-        const uint4 v = vp[n * 32 + lane];
-        mma16816(O[n], pl, v.x, v.y);
-        mma16816(O[n], ph, v.z, v.w);
-        mma16816(O[n], ph, v.x, v.y);
+      for (int n0 = 0; n0 < VNT; n0 += 7) {            // 7 independent accumulator chains in flight
+        uint4 v[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) v[q] = vp[(n0 + q) * 32 + lane];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) mma16816(O[n0 + q], pl, v[q].x, v[q].y);
+#pragma unroll
+        for (int q = 0; q < 7; ++q) mma16816(O[n0 + q], ph, v[q].z, v[q].w);
+#pragma unroll
+        for (int q = 0; q < 7; ++q) mma16816(O[n0 + q], ph, v[q].x, v[q].y);
       }
     }
     __syncthreads();                                   // (B) P tile and alpha complete

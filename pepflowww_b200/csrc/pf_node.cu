@@ -73,7 +73,8 @@ __global__ void add_layernorm_kernel(const float* __restrict__ a, const float* _
 // ---------------------------------------------------------------- K5: transformer attention core
 // CTA = (head, complex); K/V of this head staged in smem; warp handles query rows i = warp, warp+8, ...
 // qkv row layout (torch in_proj): q(128) | k(128) | v(128), head h at columns h*32 .. h*32+31.
-constexpr int TFH = 4, TFD = 32;
+constexpr int TFH = 4;
+constexpr int SEQ_ROWS = 64;   // query rows per CTA (grid.z chunks; K/V of the head are re-staged per chunk)
 __global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restrict__ qkv,
                                                             const float* __restrict__ mask,
                                                             float* __restrict__ ctx, int L) {
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restr
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
   float* P = Ps + (size_t)warp * L;
   float* Q = Qs + warp * 32;
-  for (int i = warp; i < L; i += 8) {
+  const int r_end = min(L, (int)(blockIdx.z + 1) * SEQ_ROWS);
+  for (int i = blockIdx.z * SEQ_ROWS + warp; i < r_end; i += 8) {
     Q[lane] = base[(size_t)i * 384 + h * 32 + lane];
     __syncwarp();
     float mx = -INFINITY;
@@ -269,7 +271,7 @@ int launch_seq_attention(const float* qkv, const float* mask, float* ctx, int B,
   if (B == 0 || L == 0) return PF_OK;
   const size_t smem = seq_attention_smem(L);
   if (smem > 227 * 1024) return PF_ERR_BAD_SHAPE;  // L <= ~780
-  seq_attention_kernel<<<dim3(TFH, B), 256, smem, st>>>(qkv, mask, ctx, L);
+  seq_attention_kernel<<<dim3(TFH, B, (L + SEQ_ROWS - 1) / SEQ_ROWS), 256, smem, st>>>(qkv, mask, ctx, L);
   PF_CHECK_LAUNCH();
   return PF_OK;
 }
