@@ -140,7 +140,7 @@ int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_poin
 
 int pf_set_option(const char* name, int value) {
   if (!name) return PF_ERR_NULL_POINTER;
-  if (!std::strcmp(name, "edge_impl") && (value == 0 || value == 1)) { pf::g_edge_impl = value; return PF_OK; }
+  if (!std::strcmp(name, "edge_impl") && (value >= 0 && value <= 2)) { pf::g_edge_impl = value; return PF_OK; }
   if (!std::strcmp(name, "gemm_impl") && (value == 0 || value == 1)) { pf::g_gemm_impl = value; return PF_OK; }
   if (!std::strcmp(name, "ipa_impl") && (value == 0 || value == 1)) { pf::g_ipa_impl = value; return PF_OK; }
   return PF_ERR_BAD_OPTION;

@@ -117,6 +117,11 @@ int launch_edge_transition(const float* s, const float* z_in, const float* w_ini
                            const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
                            const float* bf, const float* ln_g, const float* ln_b, const float* mask, float* z_out,
                            void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st);
+void edge_umma_init();
+size_t edge_umma_pack_bytes();
+int launch_edge_umma(const float* z_in, const float* P, const float* Q, const float* U, const float* V,
+                     const float* w1, const float* w2, const float* wf, const float* b2, const float* ln_g,
+                     const float* ln_b, const float* mask, float* z_out, void* wpack, int B, int L, cudaStream_t st);
 void node_kernels_init();
 void ipa_kernels_init();
 void edge_kernels_init();

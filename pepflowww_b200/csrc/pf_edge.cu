@@ -420,6 +420,7 @@ constexpr size_t E0_SMEM = (size_t)(2 * E0_ROWS * E0_XS + 16 * E0_WS) * sizeof(f
 void edge_kernels_init() {
   cudaFuncSetAttribute(edge_transition_v0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E0_SMEM);
   cudaFuncSetAttribute(edge_transition_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E1_SMEM);
+  edge_umma_init();
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -427,7 +428,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t edge_workspace_bytes(int B, int L) {
   const size_t M = (size_t)B * L;
   return align256(M * 64 * 4) + 2 * align256(M * 192 * 4) + 2 * align256(M * 64 * 4) + align256(E1_W2_BYTES) +
-         align256(E1_STREAM_BYTES);
+         align256(E1_STREAM_BYTES) + align256(edge_umma_pack_bytes());
 }
 
 int launch_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,
@@ -454,11 +455,14 @@ int launch_edge_transition(const float* s, const float* z_in, const float* w_ini
   float* U = reinterpret_cast<float*>(ws); ws += align256((size_t)M * 64 * 4);
   float* V = reinterpret_cast<float*>(ws); ws += align256((size_t)M * 64 * 4);
   uint4* w2pack = reinterpret_cast<uint4*>(ws); ws += align256(E1_W2_BYTES);
-  uint4* stream = reinterpret_cast<uint4*>(ws);
+  uint4* stream = reinterpret_cast<uint4*>(ws); ws += align256(E1_STREAM_BYTES);
+  void* upack = ws;
   PF_TRY(launch_linear_ld(e, w1 + 64, 192, b1, P, M, 64, 192, st));
   PF_TRY(launch_linear_ld(e, w1 + 128, 192, nullptr, Q, M, 64, 192, st));
   PF_TRY(launch_linear_ld(e, wf + 64, 192, bf, U, M, 64, 64, st));
   PF_TRY(launch_linear_ld(e, wf + 128, 192, nullptr, V, M, 64, 64, st));
+  if (opt_edge_impl() == 2)
+    return launch_edge_umma(z_in, P, Q, U, V, w1, w2, wf, b2, ln_g, ln_b, mask, z_out, upack, B, L, st);
   {
     const int n = (E1_W2_BYTES + E1_STREAM_BYTES) / 16;
     edge_pack_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w1, w2, wf, w2pack, stream);
