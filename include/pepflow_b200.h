@@ -61,6 +61,10 @@ void pf_reset_launch_count(void);
 int pf_profile_enable(int on);
 int pf_profile_read(double* ipa_ms, int64_t* ipa_launches, double* edge_ms, int64_t* edge_launches);
 
+/* Diagnostics: while a device buffer is registered, instrumented kernel variants write clock64() stamps of
+ * their internal hand-offs into it (layout documented at the kernel).  NULL unregisters.  Not a hot-path call. */
+int pf_debug_buffer(void* device_buffer, size_t bytes);
+
 /* ---- generic node-level ops --------------------------------------------------------------- */
 /* y[M,N] = act(x[M,K] W[N,K]^T + bias) (+ residual[M,N]) (* rowmask[M]).   act: 0 none, 1 ReLU.
  * Replaces models_con/ipa_pytorch.py:116-181 (Linear) and the nn.Linear layers of ga.py:22-45. */

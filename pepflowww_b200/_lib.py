@@ -27,6 +27,7 @@ SIGNATURES = {
     "pf_get_option": (_i, [C.c_char_p]),
     "pf_launch_count": (C.c_int64, []),
     "pf_reset_launch_count": (None, []),
+    "pf_debug_buffer": (_i, [_p, _sz]),
     "pf_profile_enable": (_i, [_i]),
     "pf_profile_read": (_i, [_p, _p, _p, _p]),
     "pf_linear": (_i, [_p] * 6 + [_i] * 4 + [_p]),

@@ -44,6 +44,9 @@ void profile_end(int c, cudaStream_t st) {
   g_open[c] = nullptr;
 }
 int num_sms() { return g_num_sms; }
+static std::atomic<void*> g_dbg_ptr{nullptr};
+static std::atomic<size_t> g_dbg_bytes{0};
+void* debug_buffer(size_t bytes) { return g_dbg_bytes.load() >= bytes ? g_dbg_ptr.load() : nullptr; }
 int opt_edge_impl() { return g_edge_impl.load(std::memory_order_relaxed); }
 int opt_gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
 int opt_ipa_impl() { return g_ipa_impl.load(std::memory_order_relaxed); }
@@ -152,6 +155,12 @@ int pf_get_option(const char* name) {
   if (!std::strcmp(name, "gemm_impl")) return pf::opt_gemm_impl();
   if (!std::strcmp(name, "ipa_impl")) return pf::opt_ipa_impl();
   return PF_ERR_BAD_OPTION;
+}
+
+int pf_debug_buffer(void* device_buffer, size_t bytes) {
+  pf::g_dbg_ptr.store(device_buffer);
+  pf::g_dbg_bytes.store(device_buffer ? bytes : 0);
+  return PF_OK;
 }
 
 int pf_profile_enable(int on) {

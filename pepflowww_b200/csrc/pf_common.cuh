@@ -27,6 +27,8 @@ void count_launch();
 void profile_begin(int category, cudaStream_t st);
 void profile_end(int category, cudaStream_t st);
 int num_sms();
+// device buffer registered with pf_debug_buffer() if it holds at least `bytes`, else nullptr
+void* debug_buffer(size_t bytes);
 int opt_edge_impl();
 int opt_gemm_impl();
 int opt_ipa_impl();
@@ -118,7 +120,7 @@ int launch_edge_transition(const float* s, const float* z_in, const float* w_ini
                            const float* bf, const float* ln_g, const float* ln_b, const float* mask, float* z_out,
                            void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st);
 void edge_umma_init();
-size_t edge_umma_pack_bytes();
+size_t edge_umma_pack_bytes(int B, int L);
 int launch_edge_umma(const float* z_in, const float* P, const float* Q, const float* U, const float* V,
                      const float* w1, const float* w2, const float* wf, const float* b2, const float* ln_g,
                      const float* ln_b, const float* mask, float* z_out, void* wpack, int B, int L, cudaStream_t st);

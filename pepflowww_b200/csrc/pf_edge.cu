@@ -428,7 +428,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t edge_workspace_bytes(int B, int L) {
   const size_t M = (size_t)B * L;
   return align256(M * 64 * 4) + 2 * align256(M * 192 * 4) + 2 * align256(M * 64 * 4) + align256(E1_W2_BYTES) +
-         align256(E1_STREAM_BYTES) + align256(edge_umma_pack_bytes());
+         align256(E1_STREAM_BYTES) + align256(edge_umma_pack_bytes(B, L));
 }
 
 int launch_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,
