@@ -252,7 +252,7 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": ipa_bytes}
     roofline_edge = None
     if edge_n:
-        passes = 3 if _lib.get_option("edge_impl") == 1 else 1
+        passes = 3 if _lib.get_option("edge_impl") in (1, 2) else 1
         flops = 172032.0 * L * L * B
         ach = flops / (edge_ms / edge_n * 1e-3) / 1e12
         roofline_edge = {"kernel": "edge_transition", "bound": "tensor" if passes == 3 else "fp32-fma",

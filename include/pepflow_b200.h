@@ -46,7 +46,8 @@ int pf_init(int device);                    /* opt kernels into >48 KB shared me
 int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_points, int no_v_points,
                     int tfmr_heads, int tfmr_layers);  /* configs/learn_angle.yaml:3-14        */
 /* Kernel variant switches (test seams, not multi-backend dispatch: every variant is sm_100a CUDA).
- *   "edge_impl": 0 = fp32 CUDA-core kernel, 1 = 3xFP16 tensor-core kernel (default)
+ *   "edge_impl": 0 = fp32 CUDA-core kernel, 1 = 3xFP16 mma.sync kernel, 2 = 3xFP16 tcgen05 kernel (CTA pairs,
+ *                operands in tensor memory; default)
  *   "gemm_impl": 0 = fp32 CUDA-core GEMM,   1 = 3xFP16 tensor-core GEMM (default)
  *   "ipa_impl" : 0 = CUDA-core attention,   1 = tensor-core attention (default when available)  */
 int pf_set_option(const char* name, int value);

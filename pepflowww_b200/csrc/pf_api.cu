@@ -12,7 +12,7 @@ namespace pf {
 
 static std::atomic<int64_t> g_launches{0};
 static int g_num_sms = 148;
-static std::atomic<int> g_edge_impl{1}, g_gemm_impl{1}, g_ipa_impl{1};
+static std::atomic<int> g_edge_impl{2}, g_gemm_impl{1}, g_ipa_impl{1};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

@@ -47,25 +47,28 @@ using namespace umma;
 constexpr int EU_THREADS = 320;        // 8 row warps + MMA / allocation warp + producer warp
 constexpr int EU_RANK_BYTES = 131072;  // packed weights per CTA rank
 // byte offsets of the weight parts inside a rank image; NL = N rows held per CTA
-constexpr int EU_NL1A = 96, EU_NL1B = 32, EU_NL2 = 96, EU_NL3 = 32;
-constexpr int EU_B1A_HI = 0, EU_B1A_LO = 12288, EU_B1B_HI = 24576, EU_B1B_LO = 28672, EU_B2_HI = 32768,
-              EU_B2_LO = 69632, EU_B3_HI = 106496, EU_B3_LO = 118784;
-constexpr uint32_t EU_COL_ACC1 = 0, EU_COL_ACC3 = 192, EU_COL_ACC2 = 256, EU_COL_A0 = 448;
+// (W2 is split by output columns into n 0..127 and n 128..191 so that the epilogue of the first part runs
+// while the second part is still on the tensor core)
+constexpr int EU_NL1A = 96, EU_NL1B = 32, EU_NL2A = 64, EU_NL2B = 32, EU_NL3 = 32;
+constexpr int EU_B1A_HI = 0, EU_B1A_LO = 12288, EU_B1B_HI = 24576, EU_B1B_LO = 28672, EU_B2A_HI = 32768,
+              EU_B2A_LO = 57344, EU_B2B_HI = 81920, EU_B2B_LO = 94208, EU_B3_HI = 106496, EU_B3_LO = 118784;
+constexpr uint32_t EU_COL_ACC1 = 0, EU_COL_ACC3 = 192, EU_COL_ACC2 = 256, EU_COL_ACC2B = 384, EU_COL_A0 = 448;
 // shared-memory map
 constexpr int EU_SMEM_SEL = EU_RANK_BYTES;            // 8192: [k/8 (4)][row (128)][16 B]
 constexpr int EU_SMEM_PQ = EU_SMEM_SEL + 8192;        // 12288: P_hi | Q_hi | P_lo | Q_lo, each [kg 2][ng 12][128 B]
 constexpr int EU_SMEM_UV = EU_SMEM_PQ + 12288;        // 4096:  U_hi | V_hi | U_lo | V_lo, each [kg 2][ng 4][128 B]
 constexpr int EU_ZBUF = 32768;                        // [half 2][i_local 16] boxes of 8 rows x 128 B
 constexpr int EU_SMEM_Z = EU_SMEM_UV + 4096;          // 2 buffers (1024-byte aligned: 128B-swizzled boxes)
-constexpr int EU_SMEM_RED = EU_SMEM_Z + 2 * EU_ZBUF;  // LayerNorm exchange: [grp 2][sum, sumsq][128 rows] floats
-constexpr int EU_SMEM_BARS = EU_SMEM_RED + 2048;
+constexpr int EU_SMEM_RED = EU_SMEM_Z + 2 * EU_ZBUF;  // LayerNorm exchange: [tile parity 2][grp 2][mean, M2][128 rows] floats
+constexpr int EU_SMEM_BARS = EU_SMEM_RED + 4096;
 static_assert(EU_SMEM_Z % 1024 == 0, "swizzled TMA boxes need 1024-byte alignment");
 // barriers
 enum {
   EU_BAR_A0 = 0,    // leader; 16 row warps: A0 of the tile staged
   EU_BAR_ACC1,      // both;   commit: acc1 complete (P/Q tile and acc1's previous content consumed)
   EU_BAR_H1,        // leader; +6, 8 row warps each: h1 chunk c in place
-  EU_BAR_ACC2 = EU_BAR_H1 + 6,   // both; commit
+  EU_BAR_ACC2A = EU_BAR_H1 + 6,  // both; commit: acc2 columns 0..127 complete
+  EU_BAR_ACC2B,     // both;   commit: acc2 columns 128..191 complete
   EU_BAR_PB,        // both;   commit: the acc3 = S[U;V] + z Wfz part is done: A0 and the U/V tile are free
   EU_BAR_H2,        // leader; +6
   EU_BAR_ACC3 = EU_BAR_H2 + 6,   // both; commit
@@ -77,8 +80,8 @@ enum {
   EU_BAR_Z,         // local;  +2, 256 row threads + transaction bytes: z tile landed in buffer b
   EU_NBARS = EU_BAR_Z + 2
 };
-constexpr int EU_SMEM_TMEM_PTR = EU_SMEM_BARS + EU_NBARS * 8;
-constexpr int EU_SMEM_B2 = EU_SMEM_TMEM_PTR + 16;     // 192 floats
+constexpr int EU_SMEM_TMEM_PTR = EU_SMEM_BARS + ((EU_NBARS * 8 + 15) & ~15);
+constexpr int EU_SMEM_B2 = EU_SMEM_TMEM_PTR + 16;     // 192 floats (16-byte aligned: vector loads)
 constexpr int EU_SMEM_LNG = EU_SMEM_B2 + 192 * 4;     // 64 floats
 constexpr int EU_SMEM_LNB = EU_SMEM_LNG + 64 * 4;     // 64 floats
 constexpr int EU_SMEM_TOTAL = EU_SMEM_LNB + 64 * 4;
@@ -103,10 +106,14 @@ __global__ void edge_umma_pack_weights_kernel(const float* __restrict__ w1, cons
     u -= 1536;
     lo = u >= 256; u %= 256;
     src = wf + (size_t)(rank * EU_NL1B + u % EU_NL1B) * 192 + (u / EU_NL1B) * 8;
-  } else if (u < 2048 + 4608) {  // B2: 2304 + 2304; unit = kc * 96 + nl
+  } else if (u < 2048 + 3072) {  // B2a (n 0..127): 1536 + 1536; unit = kc * 64 + nl
     u -= 2048;
-    lo = u >= 2304; u %= 2304;
-    src = w2 + (size_t)(rank * EU_NL2 + u % EU_NL2) * 192 + (u / EU_NL2) * 8;
+    lo = u >= 1536; u %= 1536;
+    src = w2 + (size_t)(rank * EU_NL2A + u % EU_NL2A) * 192 + (u / EU_NL2A) * 8;
+  } else if (u < 2048 + 4608) {  // B2b (n 128..191): 768 + 768; unit = kc * 32 + nl
+    u -= 2048 + 3072;
+    lo = u >= 768; u %= 768;
+    src = w2 + (size_t)(128 + rank * EU_NL2B + u % EU_NL2B) * 192 + (u / EU_NL2B) * 8;
   } else {                   // B3: 768 + 768; unit = kc * 32 + nl
     u -= 2048 + 4608;
     lo = u >= 768; u %= 768;
@@ -242,9 +249,9 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + EU_SMEM_BARS;
   auto bar = [&](int i) { return bars + 8u * i; };
-  float* sB2 = reinterpret_cast<float*>(smem + EU_SMEM_B2);
-  float* sG = reinterpret_cast<float*>(smem + EU_SMEM_LNG);
-  float* sBt = reinterpret_cast<float*>(smem + EU_SMEM_LNB);
+  float* sB2 = reinterpret_cast<float*>(__builtin_assume_aligned(smem + EU_SMEM_B2, 16));
+  float* sG = reinterpret_cast<float*>(__builtin_assume_aligned(smem + EU_SMEM_LNG, 16));
+  float* sBt = reinterpret_cast<float*>(__builtin_assume_aligned(smem + EU_SMEM_LNB, 16));
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + EU_SMEM_TMEM_PTR);
   volatile float* sRed = reinterpret_cast<volatile float*>(smem + EU_SMEM_RED);
 
@@ -255,7 +262,8 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
   if (tid == 0) {
     mbar_init(bar(EU_BAR_A0), 16);
     mbar_init(bar(EU_BAR_ACC1), 1);
-    mbar_init(bar(EU_BAR_ACC2), 1);
+    mbar_init(bar(EU_BAR_ACC2A), 1);
+    mbar_init(bar(EU_BAR_ACC2B), 1);
     mbar_init(bar(EU_BAR_PB), 1);
     mbar_init(bar(EU_BAR_ACC3), 1);
     mbar_init(bar(EU_BAR_ACC3F), 16);
@@ -385,19 +393,23 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) y[q] = __uint_as_float(r[q]);
       }
+      // LayerNorm statistics: each group reduces its own 32 channels (mean, M2 about that mean); the two halves
+      // are merged with the pairwise update of Chan et al.; only the two warps that share the rows synchronise.
       float s = 0.f;
 #pragma unroll
       for (int q = 0; q < 32; q += 4) s += (y[q] + y[q + 1]) + (y[q + 2] + y[q + 3]);
-      // exchange partial sums with the other group (same row, other 32 channels)
-      sRed[(grp * 2 + 0) * 128 + rl] = s;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-      const float mu = (s + sRed[((grp ^ 1) * 2 + 0) * 128 + rl]) * (1.0f / 64.0f);
-      float ss = 0.f;
+      const float mean_g = s * (1.0f / 32.0f);
+      float m2_g = 0.f;
 #pragma unroll
-      for (int q = 0; q < 32; ++q) { const float d = y[q] - mu; ss += d * d; }
-      sRed[(grp * 2 + 1) * 128 + rl] = ss;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-      const float rstd = 1.0f / sqrtf((ss + sRed[((grp ^ 1) * 2 + 1) * 128 + rl]) * (1.0f / 64.0f) + 1e-5f);
+      for (int q = 0; q < 32; ++q) { const float d = y[q] - mean_g; m2_g += d * d; }
+      volatile float* red = sRed + (n & 1u) * 512;
+      red[(grp * 2 + 0) * 128 + rl] = mean_g;
+      red[(grp * 2 + 1) * 128 + rl] = m2_g;
+      asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quad) : "memory");
+      const float mean_o = red[((grp ^ 1) * 2 + 0) * 128 + rl], m2_o = red[((grp ^ 1) * 2 + 1) * 128 + rl];
+      const float mu = 0.5f * (mean_g + mean_o);
+      const float dm = mean_o - mean_g;
+      const float rstd = 1.0f / sqrtf((m2_g + m2_o + dm * dm * 16.0f) * (1.0f / 64.0f) + 1e-5f);
       {
         unsigned char* op = my_rowp + obuf * EU_ZBUF;
         const float* gG = sG + 32 * grp;
@@ -430,6 +442,22 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
     uint32_t it = 0;
     float pm_prev = 0.f;
     uint32_t blk_prev = 0;
+    // one 32-column chunk of a hidden layer: fp32 accumulator -> relu(. + bias) -> packed fp16 hi | lo in place
+    auto convert_chunk = [&](uint32_t col, const uint32_t (&r)[32], const float* bias, uint32_t done_bar) {
+      float v[32];
+      if (bias) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = fmaxf(__uint_as_float(r[q]) + bias[q], 0.f);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = fmaxf(__uint_as_float(r[q]), 0.f);
+      }
+      store_split_chunk(tmem + tlane + col, v);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(done_bar, 0);
+    };
     for (uint32_t blk = first; blk < nblk; blk += stride, ++it) {
       const uint32_t ph = it & 1u;
       stamp(it, 0);
@@ -448,51 +476,53 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
         for (int k = 0; k < 3; ++k) {
           const int c = grp + 2 * k;
           tc_wait_ld();
-          float v[32];
+          uint32_t rc[32];
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = fmaxf(__uint_as_float(r[q]), 0.f);
+          for (int q = 0; q < 32; ++q) rc[q] = r[q];
           if (k < 2) tmem_ld32(tmem + tlane + EU_COL_ACC1 + 32 * (c + 2), r);
-          store_split_chunk(tmem + tlane + EU_COL_ACC1 + 32 * c, v);
-          tc_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(bar(EU_BAR_H1 + c), 0);
+          convert_chunk(EU_COL_ACC1 + 32 * c, rc, nullptr, bar(EU_BAR_H1 + c));
           stamp(it, 3 + k);
         }
       }
 
-      // ---- next tile's A0 while the long second layer runs: A0 is free once the acc3 part has consumed it
+      // ---- next tile's A0 while layer 2 runs: A0 is free once the acc3 part of this tile has consumed it
       mbar_wait(bar(EU_BAR_PB), ph);
       if (blk + stride < nblk) stage_a0(blk + stride, it + 1);
-      // z buffer it&1: its z was consumed by stage_a0(it), the previous tile's output has been staged in it;
-      // once the bulk store has read it, refill it with the z of tile it+2
-      if (it > 0) bulk_wait_read0();
-      request_z(blk + 2 * stride, it & 1u);
       stamp(it, 1);
 
-      // ---- epilogue 2: h2 = relu(acc2 + b2)
-      mbar_wait(bar(EU_BAR_ACC2), ph);
+      // ---- epilogue 2: h2 = relu(acc2 + b2); columns 0..127 while columns 128..191 are still being computed
+      mbar_wait(bar(EU_BAR_ACC2A), ph);
       tc_fence_after();
       stamp(it, 6);
       {
         uint32_t r[32];
         tmem_ld32(tmem + tlane + EU_COL_ACC2 + 32 * grp, r);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 2; ++k) {
           const int c = grp + 2 * k;
           tc_wait_ld();
-          float v[32];
+          uint32_t rc[32];
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = fmaxf(__uint_as_float(r[q]) + sB2[32 * c + q], 0.f);
-          if (k < 2) tmem_ld32(tmem + tlane + EU_COL_ACC2 + 32 * (c + 2), r);
-          store_split_chunk(tmem + tlane + EU_COL_ACC2 + 32 * c, v);
-          tc_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(bar(EU_BAR_H2 + c), 0);
+          for (int q = 0; q < 32; ++q) rc[q] = r[q];
+          if (k < 1) tmem_ld32(tmem + tlane + EU_COL_ACC2 + 32 * (c + 2), r);
+          convert_chunk(EU_COL_ACC2 + 32 * c, rc, sB2 + 32 * c, bar(EU_BAR_H2 + c));
           stamp(it, 7 + k);
         }
       }
+      mbar_wait(bar(EU_BAR_ACC2B), ph);
+      tc_fence_after();
+      {
+        const int c = 4 + grp;
+        uint32_t r[32];
+        tmem_ld32(tmem + tlane + EU_COL_ACC2 + 32 * c, r);
+        tc_wait_ld();
+        convert_chunk(EU_COL_ACC2 + 32 * c, r, sB2 + 32 * c, bar(EU_BAR_H2 + c));
+        stamp(it, 9);
+      }
+      // z buffer it&1: its z was consumed by stage_a0(it) and the previous tile's output was staged in it at the
+      // top of this iteration; once the TMA store has read it, refill it with the z of tile it+2
+      if (it > 0) bulk_wait_read0();
+      request_z(blk + 2 * stride, it & 1u);
       pm_prev = pm_cur;
       blk_prev = blk;
     }
@@ -504,39 +534,48 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
     // one elected lane issues the MMAs and commits.
     const uint32_t id_w = idesc_f16(256, 192), id_o = idesc_f16(256, 64);
     const uint32_t id_sw = id_w | (1u << 16), id_so = id_o | (1u << 16);   // selector: B operand is MN-major
-    uint32_t it = 0;
-    for (uint32_t blk = first; blk < nblk; blk += stride, ++it) {
-      const uint32_t ph = it & 1u;
-      // layer 1: acc1 = S [P;Q] + A0 W1z^T
-      mbar_wait(bar(EU_BAR_PQR), ph);
-      mbar_wait(bar(EU_BAR_A0), ph);
+    const uint32_t id_a = idesc_f16(256, 128);
+    // Tensor-pipe order per tile n:  A(n) B(n) | 2a(n) 2b(n) 3(n) | A(n+1) B(n+1) ...
+    //   A(n): acc1 = S [P;Q] + A0 W1z^T          B(n): acc3 = S [U;V] + A0 Wfz^T  (releases A0 and the U/V tile)
+    auto first_layer = [&](uint32_t n) {
+      mbar_wait(bar(EU_BAR_PQR), n & 1u);
+      mbar_wait(bar(EU_BAR_A0), n & 1u);
       tc_fence_after();
-      stamp(it, 0);
       issue_selector(tmem + EU_COL_ACC1, sbase + EU_SMEM_SEL, sbase + EU_SMEM_PQ, 12, id_sw);
       issue_chunk(tmem + EU_COL_ACC1, tmem + EU_COL_A0, sbase + EU_B1A_HI, sbase + EU_B1A_LO, 0, EU_NL1A, id_w, false);
       issue_chunk(tmem + EU_COL_ACC1, tmem + EU_COL_A0 + 32, sbase + EU_B1A_HI, sbase + EU_B1A_LO, 2, EU_NL1A, id_w, false);
       if (elect_one()) commit_pair(bar(EU_BAR_ACC1));
       __syncwarp();
-      stamp(it, 1);
-      // z / hoisted part of layer 3: acc3 = S [U;V] + A0 Wfz^T, once the previous tile's acc3 has been read;
-      // issued now so that A0 is released early (the next tile's z is staged while layer 2 runs)
-      mbar_wait(bar(EU_BAR_UVR), ph);
-      if (it > 0) mbar_wait(bar(EU_BAR_ACC3F), (it - 1) & 1u);
+      // acc3 of the previous tile must have been read by its LayerNorm epilogue
+      mbar_wait(bar(EU_BAR_UVR), n & 1u);
+      if (n > 0) mbar_wait(bar(EU_BAR_ACC3F), (n - 1) & 1u);
       tc_fence_after();
       issue_selector(tmem + EU_COL_ACC3, sbase + EU_SMEM_SEL, sbase + EU_SMEM_UV, 4, id_so);
       issue_chunk(tmem + EU_COL_ACC3, tmem + EU_COL_A0, sbase + EU_B1B_HI, sbase + EU_B1B_LO, 0, EU_NL1B, id_o, false);
       issue_chunk(tmem + EU_COL_ACC3, tmem + EU_COL_A0 + 32, sbase + EU_B1B_HI, sbase + EU_B1B_LO, 2, EU_NL1B, id_o, false);
       if (elect_one()) commit_pair(bar(EU_BAR_PB));
       __syncwarp();
-      // layer 2: acc2 = h1 W2^T, K chunk by K chunk as epilogue 1 produces h1
+    };
+    uint32_t it = 0;
+    if (first < nblk) first_layer(0);
+    for (uint32_t blk = first; blk < nblk; blk += stride, ++it) {
+      const uint32_t ph = it & 1u;
+      stamp(it, 0);
+      // layer 2, output columns 0..127: K chunk by K chunk as epilogue 1 produces h1
       for (int c = 0; c < 6; ++c) {
         mbar_wait(bar(EU_BAR_H1 + c), ph);
         tc_fence_after();
         stamp(it, 2 + c);
-        issue_chunk(tmem + EU_COL_ACC2, tmem + EU_COL_ACC1 + 32 * c, sbase + EU_B2_HI, sbase + EU_B2_LO, 2 * c, EU_NL2,
-                    id_w, c == 0);
+        issue_chunk(tmem + EU_COL_ACC2, tmem + EU_COL_ACC1 + 32 * c, sbase + EU_B2A_HI, sbase + EU_B2A_LO, 2 * c, EU_NL2A,
+                    id_a, c == 0);
       }
-      if (elect_one()) commit_pair(bar(EU_BAR_ACC2));
+      if (elect_one()) commit_pair(bar(EU_BAR_ACC2A));
+      __syncwarp();
+      // layer 2, output columns 128..191 (the epilogue of columns 0..127 runs underneath)
+      for (int c = 0; c < 6; ++c)
+        issue_chunk(tmem + EU_COL_ACC2B, tmem + EU_COL_ACC1 + 32 * c, sbase + EU_B2B_HI, sbase + EU_B2B_LO, 2 * c, EU_NL2B,
+                    id_o, c == 0);
+      if (elect_one()) commit_pair(bar(EU_BAR_ACC2B));
       __syncwarp();
       stamp(it, 8);
       // layer 3: acc3 += h2 Wf^T
@@ -550,6 +589,9 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
       if (elect_one()) commit_pair(bar(EU_BAR_ACC3));
       __syncwarp();
       stamp(it, 15);
+      // next tile's first layer (its epilogue-3-of-this-tile runs underneath)
+      if (blk + stride < nblk) first_layer(it + 1);
+      stamp(it, 1);
     }
   } else if (warp == 9 && lane == 0) {
     // ================================ producer of the P/Q and U/V tiles (both CTAs) ================

@@ -33,8 +33,8 @@ def model(dev, state_dict):
     return m.to(dev)
 
 
-@pytest.fixture(params=[(0, 0, 0), (1, 1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1)],
-                ids=["fp32", "tc", "edge_tc", "gemm_tc", "ipa_tc"])
+@pytest.fixture(params=[(0, 0, 0), (2, 1, 1), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 0, 1)],
+                ids=["fp32", "tc", "edge_mma_sync", "edge_tcgen05", "gemm_tc", "ipa_tc"])
 def impl(request):
     from pepflowww_b200 import _lib
     edge, gemm, ipa = request.param
@@ -42,7 +42,7 @@ def impl(request):
     _lib.set_option("gemm_impl", gemm)
     _lib.set_option("ipa_impl", ipa)
     yield request.param
-    _lib.set_option("edge_impl", 1)
+    _lib.set_option("edge_impl", 2)
     _lib.set_option("gemm_impl", 1)
     _lib.set_option("ipa_impl", 1)
 
@@ -266,22 +266,32 @@ def test_se3_equivariance_full_size(dev, model):
     assert rel_err(o2[3], o1[3]) < 2e-3
 
 
-def test_edge_variants_agree_full_size(dev, model):
-    """cfg4 residue count: the tensor-core edge kernel against the fp32 kernel on the same input."""
+@pytest.mark.parametrize("shape", [(2, 271), (1, 16), (3, 37), (1, 7), (2, 140), (5, 64)])
+def test_edge_variants_agree_full_size(dev, model, shape):
+    """cfg4 / cfg2 residue counts and ragged tile edges: the tensor-core edge kernels (mma.sync and tcgen05)
+    against the fp32 kernel on the same input, out of place and in place, with a residue mask."""
     from pepflowww_b200 import _lib
-    B, L = 2, 271
+    B, L = shape
     g = torch.Generator().manual_seed(2)
     s, z = torch.randn(B, L, 128, generator=g).to(dev), torch.randn(B, L, L, 64, generator=g).to(dev)
+    m = (torch.rand(B, L, generator=g) > 0.2).float().to(dev)
     et = model.ga_encoder.trunk["edge_transition_1"]
     try:
         with torch.no_grad():
             _lib.set_option("edge_impl", 0)
             a = et(s, z)
-            _lib.set_option("edge_impl", 1)
-            b = et(s, z)
+            am = et(s, z, edge_mask_rows=m)
+            for impl in (1, 2):
+                _lib.set_option("edge_impl", impl)
+                b = et(s, z)
+                assert rel_err(b, a) < 5e-5, impl
+                zz = z.clone()
+                bm = et(s, zz, edge_mask_rows=m, out=zz)
+                assert bm.data_ptr() == zz.data_ptr()
+                assert rel_err(bm, am) < 5e-5, impl
     finally:
-        _lib.set_option("edge_impl", 1)
-    assert rel_err(b, a) < 5e-5
+        _lib.set_option("edge_impl", 2)
+    assert torch.isfinite(a).all()
 
 
 # ------------------------------------------------------------------------------------------------ sampling loop
