@@ -1,6 +1,7 @@
 // Per-residue (O(L)) kernels of the denoiser: input feature mix, residual+LayerNorm, sequence
 // transformer attention core, rigid-frame update, IPA point projection into the global frame.
 #include "pf_common.cuh"
+#include "pf_split.cuh"
 
 namespace pf {
 
@@ -73,56 +74,161 @@ __global__ void add_layernorm_kernel(const float* __restrict__ a, const float* _
 // ---------------------------------------------------------------- K5: transformer attention core
 // CTA = (head, complex); K/V of this head staged in smem; warp handles query rows i = warp, warp+8, ...
 // qkv row layout (torch in_proj): q(128) | k(128) | v(128), head h at columns h*32 .. h*32+31.
+//
+// Flash-style on the tensor cores (mma.sync m16n8k16, 3xFP16 split precision, fp32 accumulate): CTA = one
+// (complex, head, block of 128 query rows); K and V^T of the head are staged once per CTA in shared memory as
+// fp16 hi / lo halves in bank-conflict-free B-fragment order; each warp owns 16 query rows and streams the keys
+// in chunks of 32 with an online softmax, re-using the score fragments as the A operand of P V.
 constexpr int TFH = 4;
-constexpr int SEQ_ROWS = 64;   // query rows per CTA (grid.z chunks; K/V of the head are re-staged per chunk)
+constexpr int SEQ_ROWS = 128;    // query rows per CTA (8 warps x 16)
+constexpr int SEQ_KW = 20;       // words (half2) per key row of K: 16 + 4 pad  -> conflict-free fragment loads
+
+__host__ __device__ inline int seq_lp(int L) { return (L + 31) & ~31; }
+__host__ __device__ inline int seq_vw(int L) { return seq_lp(L) / 2 + 12; }   // words per d row of V^T
+
 __global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restrict__ qkv,
                                                             const float* __restrict__ mask,
                                                             float* __restrict__ ctx, int L) {
-  extern __shared__ float smem[];
-  float* Ks = smem;                      // [L][33]
-  float* Vs = Ks + (size_t)L * 33;       // [L][33]
-  float* Ps = Vs + (size_t)L * 33;       // [8][L]
-  float* Qs = Ps + (size_t)8 * L;        // [8][32]
-  float* Ms = Qs + 8 * 32;               // [L]
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  const int Lp = seq_lp(L), VW = seq_vw(L);
+  uint32_t* Kh = smem_u;                   // [Lp][SEQ_KW]   half2 (c, c+1)
+  uint32_t* Kl = Kh + (size_t)Lp * SEQ_KW;
+  uint32_t* Vh = Kl + (size_t)Lp * SEQ_KW; // [32 d][VW]     half2 (key, key+1)
+  uint32_t* Vl = Vh + (size_t)32 * VW;
+  float* Ms = reinterpret_cast<float*>(Vl + (size_t)32 * VW);   // [Lp] additive key mask: 0 or -inf
   const int h = blockIdx.x, b = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const float* base = qkv + (size_t)b * L * 384;
-  for (int idx = tid; idx < L * 32; idx += 256) {
-    const int j = idx >> 5, c = idx & 31;
-    Ks[j * 33 + c] = base[(size_t)j * 384 + 128 + h * 32 + c];
-    Vs[j * 33 + c] = base[(size_t)j * 384 + 256 + h * 32 + c];
+
+  // ---- stage K (row-major pairs along c) and V^T (pairs along the key index)
+  for (int idx = tid; idx < Lp * 16; idx += 256) {
+    const int j = idx >> 4, w = idx & 15;
+    float2 k2 = make_float2(0.f, 0.f);
+    if (j < L) k2 = *reinterpret_cast<const float2*>(base + (size_t)j * 384 + 128 + h * 32 + 2 * w);
+    uint32_t hi, lo;
+    split_pair(k2.x, k2.y, hi, lo);
+    Kh[j * SEQ_KW + w] = hi;
+    Kl[j * SEQ_KW + w] = lo;
   }
-  for (int j = tid; j < L; j += 256) Ms[j] = mask[(size_t)b * L + j];
-  __syncthreads();
-  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
-  float* P = Ps + (size_t)warp * L;
-  float* Q = Qs + warp * 32;
-  const int r_end = min(L, (int)(blockIdx.z + 1) * SEQ_ROWS);
-  for (int i = blockIdx.z * SEQ_ROWS + warp; i < r_end; i += 8) {
-    Q[lane] = base[(size_t)i * 384 + h * 32 + lane];
-    __syncwarp();
-    float mx = -INFINITY;
-    for (int j = lane; j < L; j += 32) {
-      float s = 0.f;
+  for (int idx = tid; idx < (Lp / 2) * 32; idx += 256) {
+    const int d = idx & 31, jp = idx >> 5, j = 2 * jp;
+    const float v0 = (j < L) ? base[(size_t)j * 384 + 256 + h * 32 + d] : 0.f;
+    const float v1 = (j + 1 < L) ? base[(size_t)(j + 1) * 384 + 256 + h * 32 + d] : 0.f;
+    uint32_t hi, lo;
+    split_pair(v0, v1, hi, lo);
+    Vh[d * VW + jp] = hi;
+    Vl[d * VW + jp] = lo;
+  }
+  for (int j = tid; j < Lp; j += 256) Ms[j] = (j < L && mask[(size_t)b * L + j] != 0.f) ? 0.f : -INFINITY;
+
+  // ---- Q fragments of this warp's 16 rows (1/sqrt(32) folded in)
+  const int i0 = blockIdx.z * SEQ_ROWS + warp * 16;
+  const int i_lo = i0 + g, i_hi = i0 + g + 8;
+  uint32_t qh[2][4], ql[2][4];
+  {
+    const float scale = 0.17677669529663687f;  // 1/sqrt(32)
 #pragma unroll
-      for (int c = 0; c < 32; ++c) s = fmaf(Q[c], Ks[j * 33 + c], s);
-      s = (Ms[j] != 0.f) ? s * scale : -INFINITY;
-      P[j] = s;
-      mx = fmaxf(mx, s);
+    for (int ks = 0; ks < 2; ++ks) {
+      const int c = ks * 16 + 2 * t;
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+      if (i_lo < L) {
+        a0 = *reinterpret_cast<const float2*>(base + (size_t)i_lo * 384 + h * 32 + c);
+        a2 = *reinterpret_cast<const float2*>(base + (size_t)i_lo * 384 + h * 32 + c + 8);
+      }
+      if (i_hi < L) {
+        a1 = *reinterpret_cast<const float2*>(base + (size_t)i_hi * 384 + h * 32 + c);
+        a3 = *reinterpret_cast<const float2*>(base + (size_t)i_hi * 384 + h * 32 + c + 8);
+      }
+      split_pair(a0.x * scale, a0.y * scale, qh[ks][0], ql[ks][0]);
+      split_pair(a1.x * scale, a1.y * scale, qh[ks][1], ql[ks][1]);
+      split_pair(a2.x * scale, a2.y * scale, qh[ks][2], ql[ks][2]);
+      split_pair(a3.x * scale, a3.y * scale, qh[ks][3], ql[ks][3]);
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < L; j += 32) {
-      const float p = (mx == -INFINITY) ? 0.f : expf(P[j] - mx);
-      P[j] = p;
-      sum += p;
+  }
+  __syncthreads();
+  if (i0 >= L) return;
+
+  float O[4][4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) { O[n][0] = O[n][1] = O[n][2] = O[n][3] = 0.f; }
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+  for (int j0 = 0; j0 < Lp; j0 += 32) {
+    // S = Q K^T for 32 keys (4 n-tiles of 8)
+    float S[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
+      const int key = j0 + nt * 8 + g;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t bh0 = Kh[key * SEQ_KW + ks * 8 + t], bh1 = Kh[key * SEQ_KW + ks * 8 + t + 4];
+        const uint32_t bl0 = Kl[key * SEQ_KW + ks * 8 + t], bl1 = Kl[key * SEQ_KW + ks * 8 + t + 4];
+        mma16816(S[nt], ql[ks], bh0, bh1);
+        mma16816(S[nt], qh[ks], bl0, bl1);
+        mma16816(S[nt], qh[ks], bh0, bh1);
+      }
     }
-    sum = warp_sum(sum);
-    __syncwarp();
-    float o = 0.f;
-    for (int j = 0; j < L; ++j) o = fmaf(P[j], Vs[j * 33 + lane], o);
-    ctx[((size_t)b * L + i) * 128 + h * 32 + lane] = (sum > 0.f) ? o / sum : 0.f;
-    __syncwarp();
+    // key-padding mask, online softmax (rows g and g+8; a row lives in the 4 lanes of a quad)
+    float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float2 mk = *reinterpret_cast<const float2*>(Ms + j0 + nt * 8 + 2 * t);
+      S[nt][0] += mk.x; S[nt][1] += mk.y; S[nt][2] += mk.x; S[nt][3] += mk.y;
+      mx_lo = fmaxf(mx_lo, fmaxf(S[nt][0], S[nt][1]));
+      mx_hi = fmaxf(mx_hi, fmaxf(S[nt][2], S[nt][3]));
+    }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
+    // rows whose keys so far are all masked keep m = -inf: use 0 as the reference point (every p becomes 0)
+    const float rf_lo = (mn_lo == -INFINITY) ? 0.f : mn_lo, rf_hi = (mn_hi == -INFINITY) ? 0.f : mn_hi;
+    const float al_lo = expf(m_lo - rf_lo), al_hi = expf(m_hi - rf_hi);
+    m_lo = mn_lo; m_hi = mn_hi;
+    float ps_lo = 0.f, ps_hi = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      S[nt][0] = expf(S[nt][0] - rf_lo); S[nt][1] = expf(S[nt][1] - rf_lo);
+      S[nt][2] = expf(S[nt][2] - rf_hi); S[nt][3] = expf(S[nt][3] - rf_hi);
+      ps_lo += S[nt][0] + S[nt][1];
+      ps_hi += S[nt][2] + S[nt][3];
+    }
+    l_lo = l_lo * al_lo + ps_lo;
+    l_hi = l_hi * al_hi + ps_hi;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { O[n][0] *= al_lo; O[n][1] *= al_lo; O[n][2] *= al_hi; O[n][3] *= al_hi; }
+    // O += P V: the score fragments of n-tiles (2k, 2k+1) are the A fragment of key step k
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t ph[4], pl[4];
+      split_pair(S[2 * ks][0], S[2 * ks][1], ph[0], pl[0]);
+      split_pair(S[2 * ks][2], S[2 * ks][3], ph[1], pl[1]);
+      split_pair(S[2 * ks + 1][0], S[2 * ks + 1][1], ph[2], pl[2]);
+      split_pair(S[2 * ks + 1][2], S[2 * ks + 1][3], ph[3], pl[3]);
+      const int w0 = (j0 >> 1) + ks * 8 + t;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int d = n * 8 + g;
+        const uint32_t bh0 = Vh[d * VW + w0], bh1 = Vh[d * VW + w0 + 4];
+        const uint32_t bl0 = Vl[d * VW + w0], bl1 = Vl[d * VW + w0 + 4];
+        mma16816(O[n], pl, bh0, bh1);
+        mma16816(O[n], ph, bl0, bl1);
+        mma16816(O[n], ph, bh0, bh1);
+      }
+    }
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float il_lo = l_lo > 0.f ? 1.0f / l_lo : 0.f, il_hi = l_hi > 0.f ? 1.0f / l_hi : 0.f;
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const int d = n * 8 + 2 * t;
+    if (i_lo < L)
+      *reinterpret_cast<float2*>(ctx + ((size_t)b * L + i_lo) * 128 + h * 32 + d) = make_float2(O[n][0] * il_lo, O[n][1] * il_lo);
+    if (i_hi < L)
+      *reinterpret_cast<float2*>(ctx + ((size_t)b * L + i_hi) * 128 + h * 32 + d) = make_float2(O[n][2] * il_hi, O[n][3] * il_hi);
   }
 }
 
@@ -265,12 +371,14 @@ int launch_add_layernorm(const float* a, const float* b, const float* gamma, con
   return PF_OK;
 }
 
-size_t seq_attention_smem(int L) { return ((size_t)L * 33 * 2 + (size_t)8 * L + 8 * 32 + L) * sizeof(float); }
+size_t seq_attention_smem(int L) {
+  return ((size_t)seq_lp(L) * SEQ_KW * 2 + (size_t)32 * seq_vw(L) * 2 + seq_lp(L)) * sizeof(uint32_t);
+}
 
 int launch_seq_attention(const float* qkv, const float* mask, float* ctx, int B, int L, cudaStream_t st) {
   if (B == 0 || L == 0) return PF_OK;
   const size_t smem = seq_attention_smem(L);
-  if (smem > 227 * 1024) return PF_ERR_BAD_SHAPE;  // L <= ~780
+  if (smem > 227 * 1024) return PF_ERR_BAD_SHAPE;  // L <= ~980
   seq_attention_kernel<<<dim3(TFH, B, (L + SEQ_ROWS - 1) / SEQ_ROWS), 256, smem, st>>>(qkv, mask, ctx, L);
   PF_CHECK_LAUNCH();
   return PF_OK;
