@@ -453,16 +453,43 @@ __global__ void __launch_bounds__(256, 1) ipa_attention_v1_kernel(Ipa1Args p) {
     f[2 * 96 + hh * PV + pnt] = lz;
     f[3 * 96 + hh * PV + pnt] = sqrtf(lx * lx + ly * ly + lz * lz + 1e-8f);
   }
-  // o_pair: down_z on the normalised a-weighted pair row (ipa_pytorch.py:469-473)
-  for (int idx = tid; idx < TQ * H * 16; idx += 256) {
-    const int d = idx & 15, hh = (idx >> 4) & 7, i = idx >> 7;
-    if (i0 + i >= L) continue;
-    const float* src = sop + (i * H + hh) * CZ;
-    const float* w = a.w_dz + d * CZ;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < CZ; ++c) acc = fmaf(w[c], src[c], acc);
-    a.feats[(rowb + i0 + i) * NFEAT + 1024 + 384 + hh * 16 + d] = acc * sl[hh * TQ + i] + a.b_dz[d];
+  // o_pair: down_z on the normalised a-weighted pair row (ipa_pytorch.py:469-473).  W_dz is staged in shared
+  // memory (the o_pt scratch of the loop above is dead after the barrier); thread = (row i, head, half of the
+  // 16 outputs): 8 independent dot products of length 64, operands read as 16-byte vectors.
+  __syncthreads();
+  float* swz = zs;                                      // [16 d][68]
+  for (int idx = tid; idx < 16 * CZ; idx += 256) swz[(idx >> 6) * ZP + (idx & 63)] = a.w_dz[idx];
+  __syncthreads();
+  {
+    const int pairidx = tid >> 1, d0 = (tid & 1) * 8;   // pairidx = i * 8 + head
+    const int i = pairidx >> 3, hh = pairidx & 7;
+    if (i0 + i < L) {
+      const float* src = sop + (i * H + hh) * CZ;
+      float acc[8];
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+#pragma unroll 4
+      for (int c = 0; c < CZ; c += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(src + c);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          const float4 w = *reinterpret_cast<const float4*>(swz + (d0 + d) * ZP + c);
+          acc[d] = fmaf(w.x, x.x, acc[d]);
+          acc[d] = fmaf(w.y, x.y, acc[d]);
+          acc[d] = fmaf(w.z, x.z, acc[d]);
+          acc[d] = fmaf(w.w, x.w, acc[d]);
+        }
+      }
+      const float inv = sl[hh * TQ + i];
+      float* out = a.feats + (rowb + i0 + i) * NFEAT + 1024 + 384 + hh * 16 + d0;
+      float4 o0, o1;
+      o0.x = acc[0] * inv + a.b_dz[d0 + 0]; o0.y = acc[1] * inv + a.b_dz[d0 + 1];
+      o0.z = acc[2] * inv + a.b_dz[d0 + 2]; o0.w = acc[3] * inv + a.b_dz[d0 + 3];
+      o1.x = acc[4] * inv + a.b_dz[d0 + 4]; o1.y = acc[5] * inv + a.b_dz[d0 + 5];
+      o1.z = acc[6] * inv + a.b_dz[d0 + 6]; o1.w = acc[7] * inv + a.b_dz[d0 + 7];
+      *reinterpret_cast<float4*>(out) = o0;
+      *reinterpret_cast<float4*>(out + 4) = o1;
+    }
   }
 }
 
