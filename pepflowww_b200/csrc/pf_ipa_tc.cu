@@ -496,7 +496,8 @@ __global__ void __launch_bounds__(256, 1) ipa_attention_v1_kernel(Ipa1Args p) {
 size_t ipa_workspace_bytes(int B, int L) {
   const size_t JT = (L + TKEY - 1) / TKEY, IT = (L + TQ - 1) / TQ;
   const size_t u4 = (size_t)B * H * (JT * (kp_tile_u4() + vp_tile_u4()) + IT * qp_tile_u4());
-  return u4 * sizeof(uint4) + 1024;
+  const size_t v1 = u4 * sizeof(uint4) + 1024, v2 = ipa_v2_workspace_bytes(B, L);
+  return v1 > v2 ? v1 : v2;   // one buffer serves whichever variant is selected
 }
 
 int launch_ipa_attention_v1(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
