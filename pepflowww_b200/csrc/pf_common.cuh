@@ -116,12 +116,16 @@ int launch_ipa_attention_v1(const IpaArgs& a, void* workspace, size_t workspace_
 void ipa_tc_kernels_init();
 size_t ipa_v2_workspace_bytes(int B, int L);
 int launch_ipa_attention_v2(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
 void ipa_v2_kernels_init();
 size_t edge_workspace_bytes(int B, int L);
 int launch_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,
                            const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
                            const float* bf, const float* ln_g, const float* ln_b, const float* mask, float* z_out,
                            void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st);
+// 128-byte CUtensorMap over a pair tensor z [B, L, L, 64] fp32 viewed as (c: 64, j: L, bi: B*L), boxes of
+// [32 c, 8 j, 1 bi] = 1 KB with the 128-byte swizzle (shared by the edge-transition and IPA kernels)
+int encode_z_map(void* tensor_map, const float* z, int B, int L);
 void edge_umma_init();
 size_t edge_umma_pack_bytes(int B, int L);
 int launch_edge_umma(const float* z_in, const float* P, const float* Q, const float* U, const float* V,

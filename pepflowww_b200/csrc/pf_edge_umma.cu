@@ -666,7 +666,8 @@ static EncodeTiledFn encode_tiled_fn() {
   }();
   return fn;
 }
-static int encode_z_map(CUtensorMap* m, const float* z, int B, int L) {
+int encode_z_map(void* tensor_map, const float* z, int B, int L) {
+  CUtensorMap* m = static_cast<CUtensorMap*>(tensor_map);
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return static_cast<int>(cudaErrorNotSupported);
   const cuuint64_t dims[3] = {64, (cuuint64_t)L, (cuuint64_t)B * L};

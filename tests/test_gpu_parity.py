@@ -33,8 +33,8 @@ def model(dev, state_dict):
     return m.to(dev)
 
 
-@pytest.fixture(params=[(0, 0, 0), (2, 1, 2), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 0, 1), (0, 0, 2)],
-                ids=["fp32", "tc", "edge_mma_sync", "edge_tcgen05", "gemm_tc", "ipa_tc_v1", "ipa_tc_v2"])
+@pytest.fixture(params=[(0, 0, 0), (2, 1, 3), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 0, 1), (0, 0, 2), (0, 0, 3)],
+                ids=["fp32", "tc", "edge_mma_sync", "edge_tcgen05", "gemm_tc", "ipa_tc_v1", "ipa_tc_v2", "ipa_tc_v3"])
 def impl(request):
     from pepflowww_b200 import _lib
     edge, gemm, ipa = request.param
@@ -44,7 +44,7 @@ def impl(request):
     yield request.param
     _lib.set_option("edge_impl", 2)
     _lib.set_option("gemm_impl", 1)
-    _lib.set_option("ipa_impl", 2)
+    _lib.set_option("ipa_impl", 3)
 
 
 def cu(g, dev, keys):
