@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 EULER_STEPS = 200
+METRIC = "sampled peptides/sec @ 200 Euler steps, 256-res pocket; IPA HBM GB/s vs peak"
 WEIGHT_SEED = 114514
 
 
@@ -165,11 +166,13 @@ def run_reference(args):
         return
     steps, warmup = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
     cb = cpu_baseline(args, steps, warmup)
-    line = {"impl": "reference", "metric": "sampled peptides/sec @ 200 Euler steps, 256-res pocket", "value": cb["value"],
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"],
             "unit": "peptides/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg4 shape: {args.pocket}-res pocket / {args.peptide}-res peptide, "
-                                   f"{EULER_STEPS} Euler steps; CPU sample of {args.cpu_batch} complexes"},
+            "config": {"workload": f"cfg4: {args.batch} complexes/GPU x {args.gpus} GPU, {args.pocket}-res pocket / "
+                                   f"{args.peptide}-res peptide (L={args.pocket + args.peptide}), {EULER_STEPS} Euler steps",
+                       "step": f"bounded CPU sample: Euler iterations over {args.cpu_batch} complexes of the same shape on "
+                               f"the host cores, extrapolated per complex"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "peptides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -198,17 +201,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from pepflowww_b200.dist_utils import max_over_ranks as _max_over_ranks, shard_range
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max_over_ranks(x, dev)
 
     model, weights = make_model(dev)
     B, K, W = args.batch, args.steps, max(args.warmup, 0)
     # this rank's shard of independent complexes (weak scaling: B per GPU, no data-path collective)
-    host_batch = synthetic_batch(B, args.pocket, args.peptide, seed=0, first_index=rank * B)
+    lo, hi = shard_range(world * B, rank, world)
+    host_batch = synthetic_batch(hi - lo, args.pocket, args.peptide, seed=0, first_index=lo)
     host_batch = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
     L = args.pocket + args.peptide
     hbm_peak, tensor_peak, peak_src = measured_peaks()
@@ -298,7 +300,7 @@ def run_ours(args):
         cb = cpu_baseline(args, steps=3, warmup=1)
     barrier()
     if rank == 0:
-        line = {"metric": "sampled peptides/sec @ 200 Euler steps, 256-res pocket; IPA HBM GB/s vs peak",
+        line = {"metric": METRIC,
                 "value": value, "unit": "peptides/s", "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"cfg4: {B} complexes/GPU x {n_gpus} GPU, {args.pocket}-res pocket / "
