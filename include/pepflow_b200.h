@@ -48,7 +48,8 @@ int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_poin
 /* Kernel variant switches (test seams, not multi-backend dispatch: every variant is sm_100a CUDA).
  *   "edge_impl": 0 = fp32 CUDA-core kernel, 1 = 3xFP16 mma.sync kernel, 2 = 3xFP16 tcgen05 kernel (CTA pairs,
  *                operands in tensor memory; default)
- *   "gemm_impl": 0 = fp32 CUDA-core GEMM,   1 = 3xFP16 tensor-core GEMM (default)
+ *   "gemm_impl": 0 = fp32 CUDA-core GEMM, 1 = 3xFP16 mma.sync GEMM, 2 = 3xFP16 tcgen05 GEMM for the K = 128
+ *                layers that are given a workspace, mma.sync otherwise (default)
  *   "ipa_impl" : 0 = CUDA-core attention, 1 = tensor-core attention (16-key tiles, fragments from L2),
  *                2 = tensor-core attention with point distances folded into Q K^T and the K/V fragments of a
  *                    key tile bulk-copied into shared memory,
@@ -74,6 +75,11 @@ int pf_debug_buffer(void* device_buffer, size_t bytes);
  * Replaces models_con/ipa_pytorch.py:116-181 (Linear) and the nn.Linear layers of ga.py:22-45. */
 int pf_linear(const float* x, const float* w, const float* bias, const float* residual, const float* rowmask,
               float* y, int M, int K, int N, int act, void* stream);
+/* Same with a caller-owned scratch buffer (>= pf_linear_workspace_bytes(N)): with "gemm_impl" = 2 the K = 128
+ * layers then run on the tcgen05 GEMM (A operand in tensor memory, pre-packed W tiles, TMA output). */
+size_t pf_linear_workspace_bytes(int N);
+int pf_linear_ws(const float* x, const float* w, const float* bias, const float* residual, const float* rowmask,
+                 float* y, int M, int K, int N, int act, void* workspace, size_t workspace_bytes, void* stream);
 /* y = LayerNorm_128(a + b) * rowmask   (b, rowmask optional).  ga.py:104, ipa_pytorch.py:203-204. */
 int pf_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, const float* rowmask,
                      float* y, int M, int N, void* stream);

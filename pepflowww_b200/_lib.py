@@ -31,6 +31,8 @@ SIGNATURES = {
     "pf_profile_enable": (_i, [_i]),
     "pf_profile_read": (_i, [_p, _p, _p, _p]),
     "pf_linear": (_i, [_p] * 6 + [_i] * 4 + [_p]),
+    "pf_linear_workspace_bytes": (_sz, [_i]),
+    "pf_linear_ws": (_i, [_p] * 6 + [_i] * 4 + [_p, _sz, _p]),
     "pf_add_layernorm": (_i, [_p] * 6 + [_i] * 2 + [_p]),
     "pf_mix_features": (_i, [_p] * 8 + [_i] * 2 + [_p]),
     "pf_ipa_points": (_i, [_p] * 4 + [_i] * 2 + [_p]),

@@ -12,7 +12,7 @@ namespace pf {
 
 static std::atomic<int64_t> g_launches{0};
 static int g_num_sms = 148;
-static std::atomic<int> g_edge_impl{2}, g_gemm_impl{1}, g_ipa_impl{3};
+static std::atomic<int> g_edge_impl{2}, g_gemm_impl{2}, g_ipa_impl{3};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -57,7 +57,8 @@ struct GaWorkspace {
   float *xmix, *s, *ta, *tb, *ya, *yb, *proj, *pts, *feats, *qkv, *ctx, *quat, *rot, *trans, *upd, *ang_raw, *zbuf;
   void* edge_ws;
   void* ipa_ws;
-  size_t edge_ws_bytes, ipa_ws_bytes, total;
+  void* gemm_ws;
+  size_t edge_ws_bytes, ipa_ws_bytes, gemm_ws_bytes, total;
 };
 
 static GaWorkspace carve(void* base, int B, int L) {
@@ -91,6 +92,8 @@ static GaWorkspace carve(void* base, int B, int L) {
   w.edge_ws = take(w.edge_ws_bytes);
   w.ipa_ws_bytes = ipa_workspace_bytes(B, L);
   w.ipa_ws = take(w.ipa_ws_bytes);
+  w.gemm_ws_bytes = linear_workspace_bytes(NPROJ);
+  w.gemm_ws = take(w.gemm_ws_bytes);
   w.total = off;
   return w;
 }
@@ -131,6 +134,7 @@ int pf_init(int device) {
   pf::ipa_tc_kernels_init();
   pf::ipa_v2_kernels_init();
   pf::edge_kernels_init();
+  pf::gemm_umma_init();
   e = cudaGetLastError();
   return e == cudaSuccess ? PF_OK : static_cast<int>(e);
 }
@@ -145,7 +149,7 @@ int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_poin
 int pf_set_option(const char* name, int value) {
   if (!name) return PF_ERR_NULL_POINTER;
   if (!std::strcmp(name, "edge_impl") && (value >= 0 && value <= 2)) { pf::g_edge_impl = value; return PF_OK; }
-  if (!std::strcmp(name, "gemm_impl") && (value == 0 || value == 1)) { pf::g_gemm_impl = value; return PF_OK; }
+  if (!std::strcmp(name, "gemm_impl") && (value >= 0 && value <= 2)) { pf::g_gemm_impl = value; return PF_OK; }
   if (!std::strcmp(name, "ipa_impl") && (value >= 0 && value <= 3)) { pf::g_ipa_impl = value; return PF_OK; }
   return PF_ERR_BAD_OPTION;
 }
@@ -220,6 +224,11 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
   cudaStream_t st = as_stream(stream);
   const int M = B * L;
   const int nb = w->num_blocks;
+  // node-level Linear: the K = 128 layers take the tcgen05 GEMM through the workspace (gemm_impl = 2)
+  auto launch_linear = [&](const float* x, const float* wt, const float* bias, const float* residual,
+                           const float* rowmask, float* y, int M_, int K_, int N_, int act, cudaStream_t s_) {
+    return launch_linear_ws(x, wt, K_, bias, residual, rowmask, y, M_, K_, N_, act, ws.gemm_ws, ws.gemm_ws_bytes, s_);
+  };
 
   // K1: feature mix (ga.py:94-95)
   PF_TRY(launch_mix_features(node_embed, w->g[PF_G_SEQ_EMB], seqs_t, t, w->g[PF_G_TIME_FREQS], angles_t,

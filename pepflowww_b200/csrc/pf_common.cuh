@@ -98,6 +98,14 @@ struct IpaArgs {
 };
 int launch_linear(const float* x, const float* w, const float* bias, const float* residual, const float* rowmask,
                   float* y, int M, int K, int N, int act, cudaStream_t st);
+size_t gemm_umma_pack_bytes(int N);
+int launch_linear_umma(const float* x, const float* w, int ldw, const float* bias, const float* rowmask, float* y,
+                       int M, int N, int act, void* wpack, cudaStream_t st);
+void gemm_umma_init();
+size_t linear_workspace_bytes(int N);
+int launch_linear_ws(const float* x, const float* w, int ldw, const float* bias, const float* residual,
+                     const float* rowmask, float* y, int M, int K, int N, int act, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
 int launch_linear_ld(const float* x, const float* w, int ldw, const float* bias, float* y, int M, int K, int N,
                      cudaStream_t st);
 int launch_mix_features(const float* node, const float* emb, const int64_t* seqs, const float* t, const float* tfreq,

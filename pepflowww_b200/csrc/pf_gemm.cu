@@ -244,7 +244,7 @@ int launch_linear_full(const float* x, const float* w, int ldw, const float* bia
                        const float* rowmask, float* y, int M, int K, int N, int act, cudaStream_t st) {
   if (M == 0 || N == 0) return PF_OK;
   const bool vec = (K % 4 == 0) && (ldw % 4 == 0) && aligned16(x) && aligned16(w);
-  if (opt_gemm_impl() == 1) {
+  if (opt_gemm_impl() >= 1) {
     dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
     if (vec) f16x3_gemm_tn_kernel<true><<<grid, 256, 0, st>>>(x, w, bias, residual, rowmask, y, M, K, N, ldw, act);
     else f16x3_gemm_tn_kernel<false><<<grid, 256, 0, st>>>(x, w, bias, residual, rowmask, y, M, K, N, ldw, act);
@@ -255,6 +255,21 @@ int launch_linear_full(const float* x, const float* w, int ldw, const float* bia
   }
   PF_CHECK_LAUNCH();
   return PF_OK;
+}
+
+// With a caller-provided workspace the K = 128 layers run on the tcgen05 GEMM ("gemm_impl" = 2); everything else
+// (and every call without workspace) takes the mma.sync / fp32 kernels above.
+size_t linear_workspace_bytes(int N) { return gemm_umma_pack_bytes(N) + 256; }
+
+int launch_linear_ws(const float* x, const float* w, int ldw, const float* bias, const float* residual,
+                     const float* rowmask, float* y, int M, int K, int N, int act, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  if (M == 0 || N == 0) return PF_OK;
+  const bool umma_ok = opt_gemm_impl() == 2 && K == 128 && N % 4 == 0 && !residual && ws &&
+                       ws_bytes >= gemm_umma_pack_bytes(N) && aligned16(x) && aligned16(y) && aligned16(ws) &&
+                       ldw % 2 == 0;
+  if (umma_ok) return launch_linear_umma(x, w, ldw, bias, rowmask, y, M, N, act, ws, st);
+  return launch_linear_full(x, w, ldw, bias, residual, rowmask, y, M, K, N, act, st);
 }
 
 int launch_linear(const float* x, const float* w, const float* bias, const float* residual, const float* rowmask,
@@ -269,6 +284,17 @@ int launch_linear_ld(const float* x, const float* w, int ldw, const float* bias,
 }
 
 }  // namespace pf
+
+extern "C" size_t pf_linear_workspace_bytes(int N) { return pf::linear_workspace_bytes(N); }
+
+extern "C" int pf_linear_ws(const float* x, const float* w, const float* bias, const float* residual,
+                            const float* rowmask, float* y, int M, int K, int N, int act, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  PF_REQUIRE(x && w && y, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(M >= 0 && K > 0 && N > 0 && (act == 0 || act == 1), PF_ERR_BAD_SHAPE);
+  return pf::launch_linear_ws(x, w, K, bias, residual, rowmask, y, M, K, N, act, workspace, workspace_bytes,
+                              pf::as_stream(stream));
+}
 
 extern "C" int pf_linear(const float* x, const float* w, const float* bias, const float* residual,
                          const float* rowmask, float* y, int M, int K, int N, int act, void* stream) {

@@ -1,0 +1,251 @@
+// Node-level Linear layers with K = 128 on the 5th-generation tensor cores ("gemm_impl" = 2):
+//   y[M,N] = act(x[M,128] W[N,128]^T + b) (* rowmask)        (models_con/ipa_pytorch.py:116-181, ga.py:22-64)
+// 3xFP16 split precision (hi*hi + lo*hi + hi*lo, fp32 accumulation in tensor memory), same arithmetic as the
+// mma.sync GEMM in pf_gemm.cu.
+//
+// One CTA per 128-row block of x.  The block is read once, split into fp16 hi | lo and parked in tensor memory
+// as the A operand (128 columns) for the whole N loop; W arrives as pre-packed 128-row tiles (fp16 hi | lo in
+// the K-major core-matrix layout, 64 KB per tile, one bulk copy each) through a 2-stage shared-memory ring; two
+// 128-column accumulators alternate so the epilogue of tile n runs under the MMAs of tile n + 1; the epilogue
+// stages the fp32 output tile in shared memory (128-byte swizzle) and stores it with tensor-map TMA, which also
+// clips the ragged M / N edges.
+// Warps 0-3: row threads (A staging, epilogue); warp 4: MMA issuer + tensor-memory allocation; warp 5: W producer.
+#include <cuda.h>
+
+#include "pf_common.cuh"
+#include "pf_split.cuh"
+#include "pf_umma.cuh"
+
+namespace pf {
+
+using namespace umma;
+
+constexpr int GU_THREADS = 192;
+constexpr int GU_TILE_BYTES = 65536;           // one W tile: hi [16 kc][128 n][16 B] | lo
+constexpr int GU_SM_W = 0;                     // 2 stages
+constexpr int GU_SM_OUT = 2 * GU_TILE_BYTES;   // 4 boxes of [128 rows][32 cols] fp32, 128-byte swizzle (64 KB)
+constexpr int GU_SM_BIAS = GU_SM_OUT + 65536;  // 128 floats of the current tile (double buffered)
+constexpr int GU_SM_BAR = GU_SM_BIAS + 2 * 128 * 4;
+enum { GU_BAR_WFULL = 0, GU_BAR_WEMPTY = 2, GU_BAR_ACCFULL = 4, GU_BAR_ACCEMPTY = 6, GU_BAR_A = 8, GU_NBARS = 9 };
+constexpr int GU_SM_TMEM = GU_SM_BAR + GU_NBARS * 8 + 8;
+constexpr int GU_SMEM = GU_SM_TMEM + 16;
+static_assert(GU_SM_OUT % 1024 == 0 && GU_SMEM <= 232448, "shared memory layout");
+constexpr uint32_t GU_COL_A = 0, GU_COL_ACC = 128;   // A: 4 chunks x (16 hi + 16 lo) columns; accumulators 2 x 128
+
+// W [N, K=128] (row stride ldw) -> tiles of 128 rows: hi [kc][n][8 halves] | lo, zero rows beyond N
+__global__ void gemm_umma_pack_kernel(const float* __restrict__ w, int ldw, int N, uint4* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte unit of the hi part
+  const int ntiles = (N + 127) / 128;
+  if (idx >= ntiles * 2048) return;
+  const int tile = idx / 2048, u = idx % 2048, kc = u / 128, nl = u % 128, n = tile * 128 + nl;
+  uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+  if (n < N) {
+    const float* src = w + (size_t)n * ldw + kc * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_pair(src[2 * q], src[2 * q + 1], hi[q], lo[q]);
+  }
+  out[(size_t)tile * 4096 + u] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  out[(size_t)tile * 4096 + 2048 + u] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+struct alignas(64) GemmUArgs {
+  CUtensorMap tm_y;          // y [M, N] fp32, box [128 rows, 32 cols], 128-byte swizzle
+  const float* x; const float* bias; const float* rowmask;
+  const uint4* wpack;
+  int M, N, ntiles, act;
+};
+
+__global__ void __launch_bounds__(GU_THREADS, 1) gemm_umma_kernel(const __grid_constant__ GemmUArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + GU_SM_BAR;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + GU_SM_TMEM);
+  float* sbias = reinterpret_cast<float*>(smem + GU_SM_BIAS);
+  const int m0 = blockIdx.x * 128;
+
+  if ((sbase & 1023u) != 0) __trap();
+  if (warp == 4) tmem_alloc_cta(sbase + GU_SM_TMEM, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(GU_BAR_WFULL + i), 1);
+      mbar_init(bar(GU_BAR_WEMPTY + i), 1);
+      mbar_init(bar(GU_BAR_ACCFULL + i), 1);
+      mbar_init(bar(GU_BAR_ACCEMPTY + i), 4);
+    }
+    mbar_init(bar(GU_BAR_A), 4);
+    fence_mbar_init();
+    tma_prefetch_desc(&a.tm_y);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const int ntiles = a.ntiles;
+
+  if (warp < 4) {
+    // ================================ row threads ================================================
+    const int rl = warp * 32 + lane, m = m0 + rl;
+    const uint32_t tlane = static_cast<uint32_t>(warp * 32) << 16;
+    // ---- A: this thread's row of x -> fp16 hi | lo chunks in tensor memory
+    {
+      const float4* xp = reinterpret_cast<const float4*>(a.x + (size_t)(m < a.M ? m : 0) * 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t4 = (m < a.M) ? __ldg(xp + c * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) split_pair(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+        tmem_st16(tmem + tlane + GU_COL_A + 32 * c, hi);
+        tmem_st16(tmem + tlane + GU_COL_A + 32 * c + 16, lo);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(GU_BAR_A));
+    }
+    const float rm = (a.rowmask && m < a.M) ? a.rowmask[m] : 1.f;
+    unsigned char* orow = smem + GU_SM_OUT + rl * 128;        // + box * 16384; 16-byte chunk q at q ^ (rl & 7)
+    const int r8 = rl & 7;
+    for (int nt = 0; nt < ntiles; ++nt) {
+      const int buf = nt & 1;
+      const uint32_t ph = (nt >> 1) & 1u;
+      // bias of this tile (written by this group before the barrier below, read after it)
+      {
+        const int n = nt * 128 + rl;
+        sbias[buf * 128 + rl] = (a.bias && n < a.N) ? a.bias[n] : 0.f;
+      }
+      mbar_wait(bar(GU_BAR_ACCFULL + buf), ph);
+      tc_fence_after();
+      // the previous tile's TMA stores must have read the staging buffer before it is overwritten
+      if (nt > 0) {
+        if (tid == 0) bulk_wait_read0();
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      const float* bs = sbias + buf * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + tlane + GU_COL_ACC + 128 * buf + 32 * c, r);
+        tc_wait_ld();
+        unsigned char* box = orow + c * 16384;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o;
+          o.x = __uint_as_float(r[4 * q]) + bs[32 * c + 4 * q];
+          o.y = __uint_as_float(r[4 * q + 1]) + bs[32 * c + 4 * q + 1];
+          o.z = __uint_as_float(r[4 * q + 2]) + bs[32 * c + 4 * q + 2];
+          o.w = __uint_as_float(r[4 * q + 3]) + bs[32 * c + 4 * q + 3];
+          if (a.act == 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          o.x *= rm; o.y *= rm; o.z *= rm; o.w *= rm;
+          *reinterpret_cast<float4*>(box + ((q ^ r8) << 4)) = o;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(GU_BAR_ACCEMPTY + buf));   // accumulator may be overwritten
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (nt * 128 + 32 * c < a.N) tma_store_2d(&a.tm_y, nt * 128 + 32 * c, m0, sbase + GU_SM_OUT + c * 16384);
+        bulk_commit();
+      }
+    }
+    if (tid == 0) bulk_wait0();
+  } else if (warp == 4) {
+    // ================================ MMA issuer ==================================================
+    const uint32_t idesc = idesc_f16(128, 128);
+    mbar_wait(bar(GU_BAR_A), 0);
+    tc_fence_after();
+    for (int nt = 0; nt < ntiles; ++nt) {
+      const int buf = nt & 1;
+      const uint32_t ph = (nt >> 1) & 1u;
+      mbar_wait(bar(GU_BAR_WFULL + buf), ph);
+      if (nt >= 2) mbar_wait(bar(GU_BAR_ACCEMPTY + buf), ((nt >> 1) - 1) & 1u);
+      tc_fence_after();
+      const uint32_t wt = sbase + GU_SM_W + buf * GU_TILE_BYTES;
+      const uint32_t d = tmem + GU_COL_ACC + 128 * buf;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t dh = smem_desc(wt + ks * 4096, 2048, 128);
+        const uint64_t dl = smem_desc(wt + 32768 + ks * 4096, 2048, 128);
+        const uint32_t a_hi = tmem + GU_COL_A + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
+        if (elect_one()) {
+          mma_cta_ts(d, a_lo, dh, idesc, ks == 0 ? 0u : 1u);
+          mma_cta_ts(d, a_hi, dl, idesc, 1u);
+          mma_cta_ts(d, a_hi, dh, idesc, 1u);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        commit_cta(bar(GU_BAR_WEMPTY + buf));     // the W stage can be refilled once these MMAs have read it
+        commit_cta(bar(GU_BAR_ACCFULL + buf));
+      }
+      __syncwarp();
+    }
+  } else if (lane == 0) {
+    // ================================ W producer ==================================================
+    for (int nt = 0; nt < ntiles; ++nt) {
+      const int buf = nt & 1;
+      if (nt >= 2) mbar_wait(bar(GU_BAR_WEMPTY + buf), ((nt >> 1) - 1) & 1u);
+      mbar_arrive_expect_tx(bar(GU_BAR_WFULL + buf), GU_TILE_BYTES);
+      bulk_g2s(sbase + GU_SM_W + buf * GU_TILE_BYTES, a.wpack + (size_t)nt * 4096, GU_TILE_BYTES, bar(GU_BAR_WFULL + buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc_cta(tmem, 512);
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_y_map(CUtensorMap* m, float* y, int M, int N) {
+  static EncodeTiledFn2 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn2>(p);
+  }();
+  if (!fn) return static_cast<int>(cudaErrorNotSupported);
+  const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)N * 4};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PF_OK : static_cast<int>(cudaErrorInvalidValue);
+}
+
+size_t gemm_umma_pack_bytes(int N) { return (size_t)((N + 127) / 128) * GU_TILE_BYTES; }
+
+// Preconditions (checked by the caller): K == 128, N % 4 == 0, x / y 16-byte aligned, no residual.
+int launch_linear_umma(const float* x, const float* w, int ldw, const float* bias, const float* rowmask, float* y,
+                       int M, int N, int act, void* wpack, cudaStream_t st) {
+  const int ntiles = (N + 127) / 128;
+  gemm_umma_pack_kernel<<<(ntiles * 2048 + 255) / 256, 256, 0, st>>>(w, ldw, N, static_cast<uint4*>(wpack));
+  PF_CHECK_LAUNCH();
+  GemmUArgs a;
+  PF_TRY(encode_y_map(&a.tm_y, y, M, N));
+  a.x = x; a.bias = bias; a.rowmask = rowmask; a.wpack = static_cast<const uint4*>(wpack);
+  a.M = M; a.N = N; a.ntiles = ntiles; a.act = act;
+  gemm_umma_kernel<<<(M + 127) / 128, GU_THREADS, GU_SMEM, st>>>(a);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+void gemm_umma_init() {
+  cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GU_SMEM);
+}
+
+}  // namespace pf

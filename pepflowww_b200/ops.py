@@ -19,6 +19,9 @@ def _c(t, dtype=F32):
     return t.contiguous()
 
 
+_linear_ws = {}
+
+
 def linear(x, w, b=None, residual=None, rowmask=None, act=0, out=None):
     """y = act(x W^T + b) (+ residual) (* rowmask[:, None]).  x [..., K], w [N, K]."""
     lib = _lib.lib_for(x.device)
@@ -29,8 +32,14 @@ def linear(x, w, b=None, residual=None, rowmask=None, act=0, out=None):
     y = out if out is not None else torch.empty(M, N, device=x.device, dtype=F32)
     res = _c(residual).reshape(M, N) if residual is not None else None
     rm = _c(rowmask).reshape(M) if rowmask is not None else None
-    check(lib.pf_linear(ptr(x2), ptr(_c(w)), ptr(_c(b), allow_none=True), ptr(res, allow_none=True),
-                        ptr(rm, allow_none=True), ptr(y), M, K, N, int(act), stream()))
+    # scratch for the tcgen05 GEMM's packed weight tiles (used when "gemm_impl" = 2 and K = 128)
+    nbytes = int(lib.pf_linear_workspace_bytes(N))
+    ws = _linear_ws.get(x.device)
+    if ws is None or ws.numel() < nbytes:
+        ws = _linear_ws[x.device] = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(lib.pf_linear_ws(ptr(x2), ptr(_c(w)), ptr(_c(b), allow_none=True), ptr(res, allow_none=True),
+                           ptr(rm, allow_none=True), ptr(y), M, K, N, int(act), ptr(ws, dtype=torch.uint8), nbytes,
+                           stream()))
     return y.reshape(*x.shape[:-1], N)
 
 

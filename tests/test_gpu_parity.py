@@ -33,8 +33,9 @@ def model(dev, state_dict):
     return m.to(dev)
 
 
-@pytest.fixture(params=[(0, 0, 0), (2, 1, 3), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 0, 1), (0, 0, 2), (0, 0, 3)],
-                ids=["fp32", "tc", "edge_mma_sync", "edge_tcgen05", "gemm_tc", "ipa_tc_v1", "ipa_tc_v2", "ipa_tc_v3"])
+@pytest.fixture(params=[(0, 0, 0), (2, 2, 3), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1), (0, 0, 2), (0, 0, 3)],
+                ids=["fp32", "tc", "edge_mma_sync", "edge_tcgen05", "gemm_mma_sync", "gemm_tcgen05", "ipa_tc_v1",
+                     "ipa_tc_v2", "ipa_tc_v3"])
 def impl(request):
     from pepflowww_b200 import _lib
     edge, gemm, ipa = request.param
@@ -43,7 +44,7 @@ def impl(request):
     _lib.set_option("ipa_impl", ipa)
     yield request.param
     _lib.set_option("edge_impl", 2)
-    _lib.set_option("gemm_impl", 1)
+    _lib.set_option("gemm_impl", 2)
     _lib.set_option("ipa_impl", 3)
 
 
@@ -55,9 +56,9 @@ GA_KEYS = ("t", "rotmats_t", "trans_t", "angles_t", "seqs_t", "node_embed", "edg
 
 
 # ------------------------------------------------------------------------------------------------ unit ops
-@pytest.mark.parametrize("gemm", [0, 1])
+@pytest.mark.parametrize("gemm", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(37, 128, 3744), (130, 629, 128), (64, 1536, 128), (5, 128, 6), (200, 128, 20),
-                                   (1, 128, 5), (257, 64, 192)])
+                                   (1, 128, 5), (257, 64, 192), (300, 128, 128), (129, 128, 384), (17344, 128, 64)])
 def test_linear(dev, gemm, shape):
     from pepflowww_b200 import _lib, ops
     _lib.set_option("gemm_impl", gemm)
@@ -71,8 +72,11 @@ def test_linear(dev, gemm, shape):
         assert rel_err(y.cpu(), ref) < 2e-5
         y2 = ops.linear(x.to(dev), w.to(dev), None)
         assert rel_err(y2.cpu(), x.double() @ w.double().t()) < 2e-5
+        # no residual: the path the tcgen05 GEMM takes for K = 128 (bias, ReLU, row mask fused)
+        y3 = ops.linear(x.to(dev), w.to(dev), b.to(dev), rowmask=rm.to(dev), act=1)
+        assert rel_err(y3.cpu(), torch.relu(x.double() @ w.double().t() + b.double()) * rm.double()[:, None]) < 2e-5
     finally:
-        _lib.set_option("gemm_impl", 1)
+        _lib.set_option("gemm_impl", 2)
 
 
 def test_add_layernorm_and_mix_features(dev, state_dict):
