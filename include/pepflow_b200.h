@@ -40,7 +40,7 @@ typedef enum pf_status {
 } pf_status;
 
 /* ---- library ---------------------------------------------------------------------------- */
-int pf_version(void);                       /* ABI version (this header: 1)                   */
+int pf_version(void);                       /* ABI version (this header: 2)                   */
 const char* pf_strerror(int status);
 int pf_init(int device);                    /* opt kernels into >48 KB shared memory, query SMs */
 int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_points, int no_v_points,
@@ -185,7 +185,15 @@ typedef struct pf_ga_weights {
   int32_t reserved;
   const float* g[PF_G_NSLOTS];
   const float* blk[PF_MAX_BLOCKS][PF_B_NSLOTS];
+  /* Optional: tensor-core images of the weights (fp16 hi/lo tiles in shared-memory order) written once by
+   * pf_ga_prepack() into a caller-owned device buffer.  NULL / 0: every call re-packs what it needs.  The
+   * caller re-runs pf_ga_prepack() after changing any weight tensor. */
+  const void* prepacked;
+  uint64_t prepacked_bytes;
 } pf_ga_weights;
+
+size_t pf_ga_prepack_bytes(const pf_ga_weights* w);
+int pf_ga_prepack(const pf_ga_weights* w, void* buffer, size_t buffer_bytes, void* stream);
 
 size_t pf_ga_encoder_workspace_bytes(int B, int L);
 /* t[B]; rot_t[B,L,9]; trans_t[B,L,3]; angles_t[B,L,5]; seqs_t[B,L] i64; node_embed[B,L,128];

@@ -28,6 +28,8 @@ SIGNATURES = {
     "pf_launch_count": (C.c_int64, []),
     "pf_reset_launch_count": (None, []),
     "pf_debug_buffer": (_i, [_p, _sz]),
+    "pf_ga_prepack_bytes": (_sz, [_p]),
+    "pf_ga_prepack": (_i, [_p, _p, _sz, _p]),
     "pf_profile_enable": (_i, [_i]),
     "pf_profile_read": (_i, [_p, _p, _p, _p]),
     "pf_linear": (_i, [_p] * 6 + [_i] * 4 + [_p]),
@@ -73,7 +75,8 @@ assert len(G_SLOTS) == PF_G_NSLOTS and len(B_SLOTS) == PF_B_NSLOTS
 
 class GaWeights(C.Structure):
     _fields_ = [("num_blocks", C.c_int32), ("reserved", C.c_int32),
-                ("g", _p * PF_G_NSLOTS), ("blk", (_p * PF_B_NSLOTS) * PF_MAX_BLOCKS)]
+                ("g", _p * PF_G_NSLOTS), ("blk", (_p * PF_B_NSLOTS) * PF_MAX_BLOCKS),
+                ("prepacked", _p), ("prepacked_bytes", C.c_uint64)]
 
 
 _lib = None

@@ -98,11 +98,63 @@ static GaWorkspace carve(void* base, int B, int L) {
   return w;
 }
 
+// ---- prepacked weight images (pf_ga_prepack) -----------------------------------------------------
+// Every K = 128 Linear that takes the tcgen05 GEMM and every block's edge-transition MLP; the order below
+// defines the offsets inside the buffer, so pf_ga_prepack and pf_ga_encoder_forward agree by construction.
+struct PackItem { const float* w; int N; size_t off; bool edge; const float* w2; const float* wf; };
+
+static size_t enumerate_packables(const pf_ga_weights* w, std::vector<PackItem>* items) {
+  size_t off = 0;
+  auto lin = [&](const float* p, int N) {
+    if (!p) return;
+    if (items) items->push_back(PackItem{p, N, off, false, nullptr, nullptr});
+    off += al(gemm_umma_pack_bytes(N));
+  };
+  lin(w->g[PF_G_MIX2_W], 128);
+  lin(w->g[PF_G_SEQNET0_W], 128); lin(w->g[PF_G_SEQNET2_W], 128); lin(w->g[PF_G_SEQNET4_W], 20);
+  lin(w->g[PF_G_ANGNET0_W], 128); lin(w->g[PF_G_ANGNET2_W], 128);
+  for (int b = 0; b < w->num_blocks; ++b) {
+    const float* const* W = w->blk[b];
+    lin(W[PF_B_PROJ_W], NPROJ);
+    for (int o : {(int)PF_B_T0_IN_W, (int)PF_B_T1_IN_W}) {
+      lin(W[o], 384); lin(W[o + 2], 128); lin(W[o + 4], 128); lin(W[o + 6], 128);
+    }
+    lin(W[PF_B_NT1_W], 128); lin(W[PF_B_NT2_W], 128); lin(W[PF_B_NT3_W], 128);
+    if (W[PF_B_ET_W1] && W[PF_B_ET_W2] && W[PF_B_ET_WF]) {
+      if (items) items->push_back(PackItem{W[PF_B_ET_W1], 0, off, true, W[PF_B_ET_W2], W[PF_B_ET_WF]});
+      off += al(edge_umma_weight_image_bytes());
+    }
+  }
+  return off;
+}
+
 }  // namespace pf
 
 extern "C" {
 
-int pf_version(void) { return 1; }
+int pf_version(void) { return 2; }
+
+size_t pf_ga_prepack_bytes(const pf_ga_weights* w) {
+  if (!w || w->num_blocks < 1 || w->num_blocks > PF_MAX_BLOCKS) return 0;
+  return pf::enumerate_packables(w, nullptr);
+}
+
+int pf_ga_prepack(const pf_ga_weights* w, void* buffer, size_t buffer_bytes, void* stream) {
+  using namespace pf;
+  PF_REQUIRE(w && buffer, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(w->num_blocks >= 1 && w->num_blocks <= PF_MAX_BLOCKS, PF_ERR_BAD_CONFIG);
+  PF_REQUIRE(aligned16(buffer), PF_ERR_MISALIGNED);
+  std::vector<PackItem> items;
+  const size_t total = enumerate_packables(w, &items);
+  PF_REQUIRE(buffer_bytes >= total, PF_ERR_WORKSPACE_TOO_SMALL);
+  unsigned char* base = static_cast<unsigned char*>(buffer);
+  cudaStream_t st = as_stream(stream);
+  for (const PackItem& it : items) {
+    if (it.edge) PF_TRY(launch_edge_umma_pack_weights(it.w, it.w2, it.wf, base + it.off, st));
+    else PF_TRY(launch_gemm_umma_pack(it.w, 128, it.N, base + it.off, st));
+  }
+  return PF_OK;
+}
 
 const char* pf_strerror(int status) {
   switch (status) {
@@ -225,9 +277,18 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
   const int M = B * L;
   const int nb = w->num_blocks;
   // node-level Linear: the K = 128 layers take the tcgen05 GEMM through the workspace (gemm_impl = 2)
+  std::vector<PackItem> packed;
+  if (w->prepacked && w->prepacked_bytes >= enumerate_packables(w, nullptr)) enumerate_packables(w, &packed);
+  auto find_packed = [&](const float* wt, bool edge) -> const void* {
+    for (const PackItem& it : packed)
+      if (it.w == wt && it.edge == edge) return static_cast<const unsigned char*>(w->prepacked) + it.off;
+    return nullptr;
+  };
   auto launch_linear = [&](const float* x, const float* wt, const float* bias, const float* residual,
                            const float* rowmask, float* y, int M_, int K_, int N_, int act, cudaStream_t s_) {
-    return launch_linear_ws(x, wt, K_, bias, residual, rowmask, y, M_, K_, N_, act, ws.gemm_ws, ws.gemm_ws_bytes, s_);
+    const void* pre = linear_umma_eligible(K_, N_, residual != nullptr) ? find_packed(wt, false) : nullptr;
+    return launch_linear_ws(x, wt, K_, bias, residual, rowmask, y, M_, K_, N_, act, ws.gemm_ws, ws.gemm_ws_bytes, s_,
+                            pre);
   };
 
   // K1: feature mix (ga.py:94-95)
@@ -284,7 +345,8 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
     if (!last) {
       PF_TRY(launch_edge_transition(ws.s, z, W[PF_B_ET_INIT_W], W[PF_B_ET_INIT_B], W[PF_B_ET_W1], W[PF_B_ET_B1],
                                     W[PF_B_ET_W2], W[PF_B_ET_B2], W[PF_B_ET_WF], W[PF_B_ET_BF], W[PF_B_ET_LN_G],
-                                    W[PF_B_ET_LN_B], res_mask, ws.zbuf, ws.edge_ws, ws.edge_ws_bytes, B, L, st));
+                                    W[PF_B_ET_LN_B], res_mask, ws.zbuf, ws.edge_ws, ws.edge_ws_bytes, B, L, st,
+                                    find_packed(W[PF_B_ET_W1], true)));
       z = ws.zbuf;
     }
   }

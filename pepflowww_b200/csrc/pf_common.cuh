@@ -99,13 +99,15 @@ struct IpaArgs {
 int launch_linear(const float* x, const float* w, const float* bias, const float* residual, const float* rowmask,
                   float* y, int M, int K, int N, int act, cudaStream_t st);
 size_t gemm_umma_pack_bytes(int N);
+int launch_gemm_umma_pack(const float* w, int ldw, int N, void* wpack, cudaStream_t st);
 int launch_linear_umma(const float* x, const float* w, int ldw, const float* bias, const float* rowmask, float* y,
-                       int M, int N, int act, void* wpack, cudaStream_t st);
+                       int M, int N, int act, const void* wpack, bool prepacked, cudaStream_t st);
 void gemm_umma_init();
 size_t linear_workspace_bytes(int N);
 int launch_linear_ws(const float* x, const float* w, int ldw, const float* bias, const float* residual,
                      const float* rowmask, float* y, int M, int K, int N, int act, void* ws, size_t ws_bytes,
-                     cudaStream_t st);
+                     cudaStream_t st, const void* prepacked = nullptr);
+bool linear_umma_eligible(int K, int N, bool has_residual);
 int launch_linear_ld(const float* x, const float* w, int ldw, const float* bias, float* y, int M, int K, int N,
                      cudaStream_t st);
 int launch_mix_features(const float* node, const float* emb, const int64_t* seqs, const float* t, const float* tfreq,
@@ -130,7 +132,8 @@ size_t edge_workspace_bytes(int B, int L);
 int launch_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,
                            const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
                            const float* bf, const float* ln_g, const float* ln_b, const float* mask, float* z_out,
-                           void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st);
+                           void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st,
+                           const void* prepacked_weights = nullptr);
 // 128-byte CUtensorMap over a pair tensor z [B, L, L, 64] fp32 viewed as (c: 64, j: L, bi: B*L), boxes of
 // [32 c, 8 j, 1 bi] = 1 KB with the 128-byte swizzle (shared by the edge-transition and IPA kernels)
 int encode_z_map(void* tensor_map, const float* z, int B, int L);
@@ -138,7 +141,10 @@ void edge_umma_init();
 size_t edge_umma_pack_bytes(int B, int L);
 int launch_edge_umma(const float* z_in, const float* P, const float* Q, const float* U, const float* V,
                      const float* w1, const float* w2, const float* wf, const float* b2, const float* ln_g,
-                     const float* ln_b, const float* mask, float* z_out, void* wpack, int B, int L, cudaStream_t st);
+                     const float* ln_b, const float* mask, float* z_out, void* wpack, int B, int L, cudaStream_t st,
+                     const void* prepacked_weights = nullptr);
+size_t edge_umma_weight_image_bytes();
+int launch_edge_umma_pack_weights(const float* w1, const float* w2, const float* wf, void* image, cudaStream_t st);
 void node_kernels_init();
 void ipa_kernels_init();
 void edge_kernels_init();

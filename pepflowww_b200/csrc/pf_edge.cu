@@ -434,7 +434,8 @@ size_t edge_workspace_bytes(int B, int L) {
 int launch_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,
                            const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
                            const float* bf, const float* ln_g, const float* ln_b, const float* mask, float* z_out,
-                           void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st) {
+                           void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st,
+                           const void* prepacked_weights) {
   if (B == 0 || L == 0) return PF_OK;
   PF_REQUIRE(workspace_bytes >= edge_workspace_bytes(B, L), PF_ERR_WORKSPACE_TOO_SMALL);
   const int M = B * L;
@@ -462,7 +463,8 @@ int launch_edge_transition(const float* s, const float* z_in, const float* w_ini
   PF_TRY(launch_linear_ld(e, wf + 64, 192, bf, U, M, 64, 64, st));
   PF_TRY(launch_linear_ld(e, wf + 128, 192, nullptr, V, M, 64, 64, st));
   if (opt_edge_impl() == 2)
-    return launch_edge_umma(z_in, P, Q, U, V, w1, w2, wf, b2, ln_g, ln_b, mask, z_out, upack, B, L, st);
+    return launch_edge_umma(z_in, P, Q, U, V, w1, w2, wf, b2, ln_g, ln_b, mask, z_out, upack, B, L, st,
+                            prepacked_weights);
   {
     const int n = (E1_W2_BYTES + E1_STREAM_BYTES) / 16;
     edge_pack_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w1, w2, wf, w2pack, stream);

@@ -685,15 +685,23 @@ size_t edge_umma_pack_bytes(int B, int L) {
   return al256(2 * (size_t)EU_RANK_BYTES) + al256(4 * lay.wide_bytes + 4 * lay.out_bytes);
 }
 
+size_t edge_umma_weight_image_bytes() { return 2 * (size_t)EU_RANK_BYTES; }
+
+int launch_edge_umma_pack_weights(const float* w1, const float* w2, const float* wf, void* image, cudaStream_t st) {
+  const int n = 2 * EU_RANK_BYTES / 16;
+  edge_umma_pack_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w1, w2, wf, static_cast<uint4*>(image));
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
 int launch_edge_umma(const float* z_in, const float* P, const float* Q, const float* U, const float* V,
                      const float* w1, const float* w2, const float* wf, const float* b2, const float* ln_g,
-                     const float* ln_b, const float* mask, float* z_out, void* wpack, int B, int L, cudaStream_t st) {
+                     const float* ln_b, const float* mask, float* z_out, void* wpack, int B, int L, cudaStream_t st,
+                     const void* prepacked_weights) {
   unsigned char* terms = static_cast<unsigned char*>(wpack) + al256(2 * (size_t)EU_RANK_BYTES);
   const PackLayout lay = pack_layout(B, L);
   {
-    const int n = 2 * EU_RANK_BYTES / 16;
-    edge_umma_pack_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w1, w2, wf, static_cast<uint4*>(wpack));
-    PF_CHECK_LAUNCH();
+    if (!prepacked_weights) PF_TRY(launch_edge_umma_pack_weights(w1, w2, wf, wpack, st));
     const size_t m = 2 * (size_t)B * 2 * lay.KG * 16 * 8;
     edge_umma_pack_terms_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(P, Q, U, V, terms, lay, B, L);
     PF_CHECK_LAUNCH();
@@ -702,7 +710,7 @@ int launch_edge_umma(const float* z_in, const float* P, const float* Q, const fl
   PF_TRY(encode_z_map(&a.tm_in, z_in, B, L));
   PF_TRY(encode_z_map(&a.tm_out, z_out, B, L));
   a.z_in = z_in; a.terms = terms; a.lay = lay; a.b2 = b2; a.ln_g = ln_g; a.ln_b = ln_b; a.mask = mask;
-  a.wpack = static_cast<const uint4*>(wpack); a.z_out = z_out; a.B = B; a.L = L;
+  a.wpack = static_cast<const uint4*>(prepacked_weights ? prepacked_weights : wpack); a.z_out = z_out; a.B = B; a.L = L;
   a.tiles_1d = (L + 15) / 16;
   a.total_blocks = B * a.tiles_1d * a.tiles_1d;
   int clusters = num_sms() / 2;

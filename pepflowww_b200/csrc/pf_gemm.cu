@@ -261,14 +261,18 @@ int launch_linear_full(const float* x, const float* w, int ldw, const float* bia
 // (and every call without workspace) takes the mma.sync / fp32 kernels above.
 size_t linear_workspace_bytes(int N) { return gemm_umma_pack_bytes(N) + 256; }
 
+bool linear_umma_eligible(int K, int N, bool has_residual) { return K == 128 && N % 4 == 0 && !has_residual; }
+
 int launch_linear_ws(const float* x, const float* w, int ldw, const float* bias, const float* residual,
                      const float* rowmask, float* y, int M, int K, int N, int act, void* ws, size_t ws_bytes,
-                     cudaStream_t st) {
+                     cudaStream_t st, const void* prepacked) {
   if (M == 0 || N == 0) return PF_OK;
-  const bool umma_ok = opt_gemm_impl() == 2 && K == 128 && N % 4 == 0 && !residual && ws &&
-                       ws_bytes >= gemm_umma_pack_bytes(N) && aligned16(x) && aligned16(y) && aligned16(ws) &&
-                       ldw % 2 == 0;
-  if (umma_ok) return launch_linear_umma(x, w, ldw, bias, rowmask, y, M, N, act, ws, st);
+  const bool shape_ok = opt_gemm_impl() == 2 && linear_umma_eligible(K, N, residual != nullptr) && aligned16(x) &&
+                        aligned16(y) && ldw % 2 == 0;
+  if (shape_ok && prepacked && aligned16(prepacked))
+    return launch_linear_umma(x, w, ldw, bias, rowmask, y, M, N, act, prepacked, true, st);
+  if (shape_ok && ws && ws_bytes >= gemm_umma_pack_bytes(N) && aligned16(ws))
+    return launch_linear_umma(x, w, ldw, bias, rowmask, y, M, N, act, ws, false, st);
   return launch_linear_full(x, w, ldw, bias, residual, rowmask, y, M, K, N, act, st);
 }
 

@@ -230,11 +230,18 @@ static int encode_y_map(CUtensorMap* m, float* y, int M, int N) {
 size_t gemm_umma_pack_bytes(int N) { return (size_t)((N + 127) / 128) * GU_TILE_BYTES; }
 
 // Preconditions (checked by the caller): K == 128, N % 4 == 0, x / y 16-byte aligned, no residual.
-int launch_linear_umma(const float* x, const float* w, int ldw, const float* bias, const float* rowmask, float* y,
-                       int M, int N, int act, void* wpack, cudaStream_t st) {
+int launch_gemm_umma_pack(const float* w, int ldw, int N, void* wpack, cudaStream_t st) {
   const int ntiles = (N + 127) / 128;
   gemm_umma_pack_kernel<<<(ntiles * 2048 + 255) / 256, 256, 0, st>>>(w, ldw, N, static_cast<uint4*>(wpack));
   PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+// wpack: scratch for the packed W tiles, or (prepacked = true) an image written earlier by launch_gemm_umma_pack
+int launch_linear_umma(const float* x, const float* w, int ldw, const float* bias, const float* rowmask, float* y,
+                       int M, int N, int act, const void* wpack, bool prepacked, cudaStream_t st) {
+  const int ntiles = (N + 127) / 128;
+  if (!prepacked) PF_TRY(launch_gemm_umma_pack(w, ldw, N, const_cast<void*>(wpack), st));
   GemmUArgs a;
   PF_TRY(encode_y_map(&a.tm_y, y, M, N));
   a.x = x; a.bias = bias; a.rowmask = rowmask; a.wpack = static_cast<const uint4*>(wpack);

@@ -111,6 +111,15 @@ class GAEncoder(nn.Module):
                          ET_LN_G=et.layer_norm.weight, ET_LN_B=et.layer_norm.bias)
             for i, name in enumerate(_lib.B_SLOTS):
                 w.blk[b][i] = P(d[name]) if name in d else None
+        # one-time tensor-core images of the weights (fp16 hi/lo tiles); redone whenever a parameter changes
+        import ctypes as C
+        lib = _lib.lib_for(dev)
+        nbytes = int(lib.pf_ga_prepack_bytes(C.byref(w)))
+        if nbytes > 0:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.pf_ga_prepack(C.byref(w), buf.data_ptr(), nbytes, _lib.stream()))
+            keep.append(buf)
+            w.prepacked, w.prepacked_bytes = buf.data_ptr(), nbytes
         self._pack, self._pack_key = (w, keep), key
         return self._pack
 
