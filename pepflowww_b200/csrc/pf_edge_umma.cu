@@ -81,8 +81,10 @@ enum {
   EU_NBARS = EU_BAR_Z + 2
 };
 constexpr int EU_SMEM_TMEM_PTR = EU_SMEM_BARS + ((EU_NBARS * 8 + 15) & ~15);
-constexpr int EU_SMEM_B2 = EU_SMEM_TMEM_PTR + 16;     // 192 floats (16-byte aligned: vector loads)
-constexpr int EU_SMEM_LNG = EU_SMEM_B2 + 192 * 4;     // 64 floats
+// b2 as B operands of one selector K step (every one of the 16 k rows = b2, so S[:, 0:16] x tile = b2 per row):
+// part a (n 0..127, 64 per CTA): hi [kg 2][ng 8][8][16 B] = 2 KB | lo 2 KB; part b (n 128..191, 32 per CTA): 1 KB | 1 KB
+constexpr int EU_SMEM_B2 = EU_SMEM_TMEM_PTR + 16;     // 6144 bytes
+constexpr int EU_SMEM_LNG = EU_SMEM_B2 + 6144;        // 64 floats
 constexpr int EU_SMEM_LNB = EU_SMEM_LNG + 64 * 4;     // 64 floats
 constexpr int EU_SMEM_TOTAL = EU_SMEM_LNB + 64 * 4;
 static_assert(EU_SMEM_TOTAL <= 232448, "shared memory budget");
@@ -238,6 +240,19 @@ __device__ __forceinline__ void issue_selector(uint32_t d_tmem, uint32_t sel, ui
   }
 }
 
+// D = S[:, 0:16] x (16 identical bias rows), hi then lo: D = bias for every row.  tile: hi | lo, each [kg 2][ng][128 B].
+__device__ __forceinline__ void issue_bias(uint32_t d_tmem, uint32_t sel, uint32_t tile, uint32_t ng, uint32_t idesc) {
+  const uint32_t piece = 2 * ng * 128, lbo = ng * 128;
+  const uint64_t da = smem_desc(sel, 2048, 128);
+  const uint64_t bh = smem_desc(tile, lbo, 128);
+  const uint64_t bl = smem_desc(tile + piece, lbo, 128);
+  if (elect_one()) {
+    mma_pair_ss(d_tmem, da, bh, idesc, 0u);
+    mma_pair_ss(d_tmem, da, bl, idesc, 1u);
+  }
+  __syncwarp();
+}
+
 // DBG: cluster 0 / CTA 0 stamps clock64() at every hand-off of its first 4 tiles into a.dbg
 // ([3 actors: row group 0, row group 1, MMA warp][4 tiles][16 events]) - see scripts/gpu_edge_timeline.py.
 template <bool DBG>
@@ -249,7 +264,6 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + EU_SMEM_BARS;
   auto bar = [&](int i) { return bars + 8u * i; };
-  float* sB2 = reinterpret_cast<float*>(__builtin_assume_aligned(smem + EU_SMEM_B2, 16));
   float* sG = reinterpret_cast<float*>(__builtin_assume_aligned(smem + EU_SMEM_LNG, 16));
   float* sBt = reinterpret_cast<float*>(__builtin_assume_aligned(smem + EU_SMEM_LNB, 16));
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + EU_SMEM_TMEM_PTR);
@@ -293,7 +307,20 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
       }
       sel[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    for (int i = tid; i < 192; i += EU_THREADS) sB2[i] = a.b2[i];
+    // b2 tiles: unit u = ((part, hi|lo), kg, ng, kr): 8 consecutive n of b2, identical for every k row
+    for (int i = tid; i < 384; i += EU_THREADS) {
+      int u = i, n0, ngs, off;
+      if (u < 256) { n0 = 64 * (int)rank; ngs = 8; off = 0; }            // part a: hi 128 units | lo 128 units
+      else { u -= 256; n0 = 128 + 32 * (int)rank; ngs = 4; off = 4096; } // part b: hi 64 | lo 64
+      const int per = 2 * ngs * 8;
+      const bool lo = u >= per;
+      const int ng = ((u % per) / 8) % ngs;
+      uint32_t hi4[4], lo4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split_pair(a.b2[n0 + ng * 8 + 2 * q], a.b2[n0 + ng * 8 + 2 * q + 1], hi4[q], lo4[q]);
+      reinterpret_cast<uint4*>(smem + EU_SMEM_B2 + off)[u] =
+          lo ? make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]) : make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+    }
     if (tid < 64) { sG[tid] = a.ln_g[tid]; sBt[tid] = a.ln_b[tid]; }
   }
   fence_proxy_async_smem();   // generic-proxy writes above are read by the tensor core through the async proxy
@@ -490,7 +517,8 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
       if (blk + stride < nblk) stage_a0(blk + stride, it + 1);
       stamp(it, 1);
 
-      // ---- epilogue 2: h2 = relu(acc2 + b2); columns 0..127 while columns 128..191 are still being computed
+      // ---- epilogue 2: h2 = relu(acc2) (b2 was added by a selector MMA); columns 0..127 while columns 128..191
+      //      are still being computed
       mbar_wait(bar(EU_BAR_ACC2A), ph);
       tc_fence_after();
       stamp(it, 6);
@@ -505,7 +533,7 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) rc[q] = r[q];
           if (k < 1) tmem_ld32(tmem + tlane + EU_COL_ACC2 + 32 * (c + 2), r);
-          convert_chunk(EU_COL_ACC2 + 32 * c, rc, sB2 + 32 * c, bar(EU_BAR_H2 + c));
+          convert_chunk(EU_COL_ACC2 + 32 * c, rc, nullptr, bar(EU_BAR_H2 + c));
           stamp(it, 7 + k);
         }
       }
@@ -516,7 +544,7 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
         uint32_t r[32];
         tmem_ld32(tmem + tlane + EU_COL_ACC2 + 32 * c, r);
         tc_wait_ld();
-        convert_chunk(EU_COL_ACC2 + 32 * c, r, sB2 + 32 * c, bar(EU_BAR_H2 + c));
+        convert_chunk(EU_COL_ACC2 + 32 * c, r, nullptr, bar(EU_BAR_H2 + c));
         stamp(it, 9);
       }
       // z buffer it&1: its z was consumed by stage_a0(it) and the previous tile's output was staged in it at the
@@ -561,20 +589,23 @@ edge_transition_umma_kernel(const __grid_constant__ EdgeUArgs a) {
     for (uint32_t blk = first; blk < nblk; blk += stride, ++it) {
       const uint32_t ph = it & 1u;
       stamp(it, 0);
+      // layer 2 starts from b2 (selector K step 0 x the constant b2 tiles; no dependence on h1)
+      issue_bias(tmem + EU_COL_ACC2, sbase + EU_SMEM_SEL, sbase + EU_SMEM_B2, 8, id_a | (1u << 16));
+      issue_bias(tmem + EU_COL_ACC2B, sbase + EU_SMEM_SEL, sbase + EU_SMEM_B2 + 4096, 4, id_so);
       // layer 2, output columns 0..127: K chunk by K chunk as epilogue 1 produces h1
       for (int c = 0; c < 6; ++c) {
         mbar_wait(bar(EU_BAR_H1 + c), ph);
         tc_fence_after();
         stamp(it, 2 + c);
         issue_chunk(tmem + EU_COL_ACC2, tmem + EU_COL_ACC1 + 32 * c, sbase + EU_B2A_HI, sbase + EU_B2A_LO, 2 * c, EU_NL2A,
-                    id_a, c == 0);
+                    id_a, false);
       }
       if (elect_one()) commit_pair(bar(EU_BAR_ACC2A));
       __syncwarp();
       // layer 2, output columns 128..191 (the epilogue of columns 0..127 runs underneath)
       for (int c = 0; c < 6; ++c)
         issue_chunk(tmem + EU_COL_ACC2B, tmem + EU_COL_ACC1 + 32 * c, sbase + EU_B2B_HI, sbase + EU_B2B_LO, 2 * c, EU_NL2B,
-                    id_o, c == 0);
+                    id_o, false);
       if (elect_one()) commit_pair(bar(EU_BAR_ACC2B));
       __syncwarp();
       stamp(it, 8);

@@ -100,7 +100,7 @@ class FlowModel(nn.Module):
 
     @torch.no_grad()
     def sampler_init(self, batch, num_steps=100, sample_bb=True, sample_ang=True, sample_seq=True, *, noise=None,
-                     uniforms=None, seed=0, encoded=None):
+                     uniforms=None, seed=0, encoded=None, stream_to_host=False):
         """Everything FlowModel.sample does before its loop (flow_model.py:229-285): encode, initial noise,
         time grid, device-resident trajectory buffers.  Returns an EulerSampler whose step(n) is one loop
         iteration - bench.py times exactly that call."""
@@ -110,7 +110,8 @@ class FlowModel(nn.Module):
         enc = encoded if encoded is not None else self.encode(batch)
         if noise is None:
             noise = self.init_noise(batch, enc, sample_bb, sample_ang, sample_seq)
-        return EulerSampler(self, batch, enc, noise, num_steps, (sample_bb, sample_ang, sample_seq), uniforms, seed)
+        return EulerSampler(self, batch, enc, noise, num_steps, (sample_bb, sample_ang, sample_seq), uniforms, seed,
+                            stream_to_host=stream_to_host)
 
     @torch.no_grad()
     def sample(self, batch, num_steps=100, sample_bb=True, sample_ang=True, sample_seq=True, *, noise=None,
@@ -119,7 +120,7 @@ class FlowModel(nn.Module):
         noise: dict from init_noise() to inject the initial state; uniforms: [num_steps, 2, B, L] injected
         U[0,1) for the two categorical draws of each step (else Philox(seed)); encoded: output of encode()."""
         smp = self.sampler_init(batch, num_steps, sample_bb, sample_ang, sample_seq, noise=noise, uniforms=uniforms,
-                                seed=seed, encoded=encoded)
+                                seed=seed, encoded=encoded, stream_to_host=True)
         for n in range(num_steps):
             smp.step(n)
         return smp.trajectory_to_host()
@@ -221,7 +222,9 @@ class EulerSampler:
     (flow_model.py:287-343; the last one is :346-372): denoiser, post-processing into the trajectory slot n,
     Euler update of the state - three C-ABI calls, no host synchronisation."""
 
-    def __init__(self, model, batch, enc, noise, num_steps, flags, uniforms, seed):
+    HOST_CHUNK = 8   # trajectory slots per device->host transfer when streaming
+
+    def __init__(self, model, batch, enc, noise, num_steps, flags, uniforms, seed, stream_to_host=False):
         dev = batch["aa"].device
         B, L = batch["aa"].shape
         f32 = lambda x: x.to(torch.float32).contiguous()
@@ -257,6 +260,26 @@ class EulerSampler:
         self.pred = (torch.empty(B, L, 3, 3, device=dev), torch.empty(B, L, 3, device=dev),
                      torch.empty(B, L, 5, device=dev), torch.empty(B, L, 20, device=dev))
         self.gt = (self.rot1, self.tr1, self.ang1, self.seq1)
+        # Streaming of the clean trajectory to pinned host memory on a side stream while the loop runs (the
+        # reference blocks on nine .cpu() calls per step, flow_model.py:313-314); torch's caching host allocator
+        # recycles the pinned blocks of trajectories the caller has dropped.
+        self.host = None
+        if stream_to_host:
+            self.host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.traj.items()}
+            self.copy_stream = torch.cuda.Stream(device=dev)
+            self._copied = 0
+
+    def _flush_to_host(self, upto):
+        """Enqueue the device->host copy of trajectory slots [self._copied, upto) behind the work issued so far."""
+        if self.host is None or upto <= self._copied:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.copy_stream.wait_event(ev)
+        with torch.cuda.stream(self.copy_stream):
+            for k, v in self.traj.items():
+                self.host[k][self._copied:upto].copy_(v[self._copied:upto], non_blocking=True)
+        self._copied = upto
 
     def step(self, n, slot=None):
         """Loop iteration n (time ts[n]); the clean prediction goes to trajectory slot `slot` (default n)."""
@@ -275,6 +298,8 @@ class EulerSampler:
             clean[2].copy_(self.ang1)
         if not sample_seq:
             clean[3].copy_(self.seq1); clean[4].copy_(self.seq1_simplex)
+        if self.host is not None and slot == n and ((n + 1) % self.HOST_CHUNK == 0 or n == self.num_steps - 1):
+            self._flush_to_host(n + 1)
         if n >= self.num_steps - 1:
             return
         d_t = float(self.ts[n + 1] - self.ts[n])
@@ -294,7 +319,11 @@ class EulerSampler:
     def trajectory_to_host(self):
         """The reference's clean_traj: list of num_steps dicts of CPU tensors (flow_model.py:313-314,371-374),
         produced by ONE device->host copy per field after the loop instead of nine .cpu() calls per step."""
-        host = {k: v.cpu() for k, v in self.traj.items()}
+        if self.host is not None and self._copied == self.num_steps:
+            self.copy_stream.synchronize()            # the streamed copies (issued during the loop) have landed
+            host = self.host
+        else:
+            host = {k: v.cpu() for k, v in self.traj.items()}
         fixed = {"rotmats_1": self.rot1.cpu(), "trans_1": self.tr1.cpu(), "angles_1": self.ang1.cpu(),
                  "seqs_1": self.seq1.cpu()}
         out = []
