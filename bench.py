@@ -179,6 +179,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel, impl, B, L):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), or None when no
+    capture matches this batch / residue count / kernel variant."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            table = json.load(f)
+    except (OSError, ValueError):
+        return None
+    for e in table.get(kernel, []):
+        if e.get("impl") == impl and e.get("B") == B and e.get("L") == L:
+            return e.get("dram_bytes")
+    return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     from pepflowww_b200 import _lib
@@ -249,7 +263,8 @@ def run_ours(args):
     if ipa_n:
         ach = ipa_bytes / (ipa_ms / ipa_n * 1e-3) / 1e9
         roofline = {"kernel": "ipa_attention", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / hbm_peak,
+                    "traffic": ncu_traffic("ipa_attention", _lib.get_option("ipa_impl"), B, L), "peak_source": peak_src,
                     "avg_launch_ms": ipa_ms / ipa_n, "launches": ipa_n, "share_of_step": ipa_ms / ms_total,
                     "algorithmic_bytes_per_launch": ipa_bytes}
     roofline_edge = None
@@ -263,7 +278,9 @@ def run_ours(args):
         ach = flops / (edge_ms / edge_n * 1e-3) / 1e12
         roofline_edge = {"kernel": "edge_transition", "bound": "tensor" if passes == 3 else "fp32-fma",
                          "achieved": ach, "peak": tensor_peak / passes, "unit": "TFLOP/s",
-                         "frac": ach / (tensor_peak / passes), "traffic": None, "peak_source": peak_src,
+                         "frac": ach / (tensor_peak / passes),
+                         "traffic": ncu_traffic("edge_transition", _lib.get_option("edge_impl"), B, L),
+                         "peak_source": peak_src,
                          "note": f"algorithmic fp32-equivalent FLOPs (131,072 per pair after hoisting; 172,032 in the "
                                  f"reference's literal formula); peak = sustained bf16 / {passes} split-precision passes",
                          "executed_tensor_tflops": ach * passes,
