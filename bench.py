@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--peptide", type=int, default=15)
     ap.add_argument("--cpu-batch", type=int, default=2, help="complexes in the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ipa-impl", type=int, default=None, help="kernel variant switch (pf_set_option), diagnostics only")
+    ap.add_argument("--edge-impl", type=int, default=None)
+    ap.add_argument("--gemm-impl", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-euler-steps", type=int, default=EULER_STEPS)
     return ap.parse_args()
@@ -220,6 +223,9 @@ def run_ours(args):
     def max_over_ranks(x):
         return _max_over_ranks(x, dev)
 
+    for name in ("ipa_impl", "edge_impl", "gemm_impl"):
+        if getattr(args, name) is not None:
+            _lib.set_option(name, getattr(args, name))
     model, weights = make_model(dev)
     B, K, W = args.batch, args.steps, max(args.warmup, 0)
     # this rank's shard of independent complexes (weak scaling: B per GPU, no data-path collective)

@@ -53,7 +53,10 @@ int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_poin
  *   "ipa_impl" : 0 = CUDA-core attention, 1 = tensor-core attention (16-key tiles, fragments from L2),
  *                2 = tensor-core attention with point distances folded into Q K^T and the K/V fragments of a
  *                    key tile bulk-copied into shared memory,
- *                3 = the same arithmetic, warp-specialised (head warps / pair warps, TMA z ring; default)  */
+ *                3 = the same arithmetic, warp-specialised (head warps / pair warps, TMA z ring),
+ *                4 = variant 3 with the pair warps decoupled (default): the pair bias of the next key tile is
+ *                    computed before the o_pair accumulation of the current one (6-slot z row ring), Q' fragments
+ *                    parked in tensor memory so the pair warps get 104 registers                            */
 int pf_set_option(const char* name, int value);
 int pf_get_option(const char* name);
 /* Launch counter: number of kernels this library has enqueued since the last reset. */

@@ -12,7 +12,7 @@ namespace pf {
 
 static std::atomic<int64_t> g_launches{0};
 static int g_num_sms = 148;
-static std::atomic<int> g_edge_impl{2}, g_gemm_impl{2}, g_ipa_impl{3};
+static std::atomic<int> g_edge_impl{2}, g_gemm_impl{2}, g_ipa_impl{4};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -202,7 +202,7 @@ int pf_set_option(const char* name, int value) {
   if (!name) return PF_ERR_NULL_POINTER;
   if (!std::strcmp(name, "edge_impl") && (value >= 0 && value <= 2)) { pf::g_edge_impl = value; return PF_OK; }
   if (!std::strcmp(name, "gemm_impl") && (value >= 0 && value <= 2)) { pf::g_gemm_impl = value; return PF_OK; }
-  if (!std::strcmp(name, "ipa_impl") && (value >= 0 && value <= 3)) { pf::g_ipa_impl = value; return PF_OK; }
+  if (!std::strcmp(name, "ipa_impl") && (value >= 0 && value <= 4)) { pf::g_ipa_impl = value; return PF_OK; }
   return PF_ERR_BAD_OPTION;
 }
 

@@ -126,7 +126,8 @@ int launch_ipa_attention_v1(const IpaArgs& a, void* workspace, size_t workspace_
 void ipa_tc_kernels_init();
 size_t ipa_v2_workspace_bytes(int B, int L);
 int launch_ipa_attention_v2(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
-int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                            bool decoupled);
 void ipa_v2_kernels_init();
 size_t edge_workspace_bytes(int B, int L);
 int launch_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,

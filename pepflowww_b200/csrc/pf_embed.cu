@@ -1,0 +1,248 @@
+// Once-per-sample pair embedder: EdgeEmbedder.forward, models_con/edge.py:39-112, as ONE
+// fused kernel.  The reference materialises [N, L, L, 225] distance features about five times (21 GB transient at
+// N = 64, L = 271) and runs ~2,400 small kernels when chunked; here nothing of size L^2 x 225 ever exists - every
+// pair goes from atom coordinates to its 64 output channels inside one thread.
+//
+//   per pair (i, j):  g_ab = exp(-softplus(coef[aa_i, aa_j])_ab * (|x_ia - x_jb| / 10)^2) * m_ia m_jb        (225)
+//                     f_d  = relu(W_d2 relu(W_d1 g + b_d1) + b_d2) * psm_ij                                    (64)
+//                     f_h  = AngularEncoding([phi_ij, psi_ij]) * psm_ij       geometry.py:393-418, layers.py:104-113 (26)
+//                     y    = W_o3 relu(W_o2 relu(T_aa[aa_i, aa_j] + same_chain * T_rel[relpos] + W_o1[:, 128:192] f_d
+//                                                + W_o1[:, 192:218] f_h + b_o1) + b_o2) + b_o3,  times mask_i mask_j
+// T_aa = aa_pair_embed W_o1[:, 0:64]^T and T_rel = relpos_embed W_o1[:, 64:128]^T are the embedding lookups pushed
+// through the first output layer (linear, so exact up to summation order); the host prepares them together with
+// softplus(coef) and the transposed weight matrices (pepflowww_b200/edge.py).
+//
+// fp32 CUDA-core kernel: 64 k FLOP per pair, 0.3 TFLOP per sample at N = 64, L = 271 - once per 200 Euler steps,
+// <0.5 % of a sampling run, so the tensor cores are not worth a split-precision pipeline here.  Persistent CTAs,
+// one query row (b, i) at a time; all weights (128 KB) stay in shared memory and are read as warp-wide broadcasts,
+// the per-row tables (softplus coefficients and T_aa rows of aa_i) are re-staged per row; a thread owns one pair and
+// keeps its activations in registers; the output tile is staged in shared memory and written as full 128-byte lines.
+#include "pf_common.cuh"
+
+namespace pf {
+
+constexpr int EE_A = 15, EE_AA = EE_A * EE_A;   // atoms per residue kept by the embedder, atom pairs
+constexpr int EE_F = 64;                        // feature width
+constexpr int EE_NH = 26;                       // dihedral encoding width: 2 angles x (1 + 6 sin + 6 cos)
+constexpr int EE_NAA = 22;                      // amino-acid slots
+constexpr int EE_NREL = 65;                     // relative positions -32..32
+constexpr int EE_MAXT = 256;                    // threads per CTA (pairs per pass), upper bound
+constexpr int EE_TP = EE_F + 1;                 // padded row of the per-pair-type tables and the output staging
+
+// shared-memory layout (floats)
+constexpr int EE_OFF_WD1 = 0;                                  // [225][64]
+constexpr int EE_OFF_WD2 = EE_OFF_WD1 + EE_AA * EE_F;          // [64][64]
+constexpr int EE_OFF_WO1D = EE_OFF_WD2 + EE_F * EE_F;          // [64][64]
+constexpr int EE_OFF_WO1H = EE_OFF_WO1D + EE_F * EE_F;         // [26][64]
+constexpr int EE_OFF_WO2 = EE_OFF_WO1H + EE_NH * EE_F;         // [64][64]
+constexpr int EE_OFF_WO3 = EE_OFF_WO2 + EE_F * EE_F;           // [64][64]
+constexpr int EE_OFF_B = EE_OFF_WO3 + EE_F * EE_F;             // b_d1 | b_d2 | b_o1 | b_o2 | b_o3
+constexpr int EE_OFF_TREL = EE_OFF_B + 5 * EE_F;               // [65][65]
+constexpr int EE_OFF_C = EE_OFF_TREL + EE_NREL * EE_TP;        // [22][225]   softplus coefficients of (aa_i, *)
+constexpr int EE_OFF_TAA = EE_OFF_C + EE_NAA * EE_AA;          // [22][65]    T_aa rows of (aa_i, *)
+constexpr int EE_OFF_PI = EE_OFF_TAA + EE_NAA * EE_TP;         // [45] x_i, [15] m_i, 4 spare
+constexpr int EE_OFF_STAGE = EE_OFF_PI + 64;                   // [T][65] output staging; aliases x_j [T][45], m_j [T][15]
+
+struct EdgeEmbedArgs {
+  const int64_t* aa;        // [N, L] (already UNK where the sequence is hidden)
+  const int64_t* res_nb;    // [N, L]
+  const int64_t* chain_nb;  // [N, L]
+  const float* pos;         // [N, L, A_in, 3]
+  const uint8_t* mask;      // [N, L, A_in]
+  const uint8_t* smask;     // [N, L] structure mask or nullptr
+  const float* csp;         // [484, 225]
+  const float* t_aa;        // [484, 64]
+  const float* t_rel;       // [65, 64]
+  const float* wd1t; const float* wd2t; const float* wo1dt; const float* wo1ht; const float* wo2t; const float* wo3t;
+  const float* bd1; const float* bd2; const float* bo1; const float* bo2; const float* bo3;
+  float* out;               // [N, L, L, 64]
+  int N, L, A_in;
+};
+
+// y[n] += x * w[n], n = 0..63: w is one row of a [K][64] matrix in shared memory (warp-wide broadcast reads)
+__device__ __forceinline__ void ee_axpy64(float (&y)[EE_F], float x, const float* __restrict__ w) {
+#pragma unroll
+  for (int n = 0; n < EE_F; n += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(w + n);
+    y[n] = fmaf(x, v.x, y[n]); y[n + 1] = fmaf(x, v.y, y[n + 1]);
+    y[n + 2] = fmaf(x, v.z, y[n + 2]); y[n + 3] = fmaf(x, v.w, y[n + 3]);
+  }
+}
+
+// geometry.py:296-313: signed dihedral of four points, NaN (degenerate geometry, e.g. padded residues) -> 0
+__device__ __forceinline__ float ee_dihedral(const float* p0, const float* p1, const float* p2, const float* p3) {
+  const float v0x = p2[0] - p1[0], v0y = p2[1] - p1[1], v0z = p2[2] - p1[2];
+  const float v1x = p0[0] - p1[0], v1y = p0[1] - p1[1], v1z = p0[2] - p1[2];
+  const float v2x = p3[0] - p2[0], v2y = p3[1] - p2[1], v2z = p3[2] - p2[2];
+  const float u1x = v0y * v1z - v0z * v1y, u1y = v0z * v1x - v0x * v1z, u1z = v0x * v1y - v0y * v1x;
+  const float u2x = v0y * v2z - v0z * v2y, u2y = v0z * v2x - v0x * v2z, u2z = v0x * v2y - v0y * v2x;
+  const float l1 = sqrtf(u1x * u1x + u1y * u1y + u1z * u1z), l2 = sqrtf(u2x * u2x + u2y * u2y + u2z * u2z);
+  const float d = (u1x / l1) * (u2x / l2) + (u1y / l1) * (u2y / l2) + (u1z / l1) * (u2z / l2);
+  if (!(d == d)) return 0.f;                       // nan_to_num
+  const float cx = v1y * v2z - v1z * v2y, cy = v1z * v2x - v1x * v2z, cz = v1x * v2y - v1y * v2x;
+  const float s = cx * v0x + cy * v0y + cz * v0z;
+  const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+  return sg * acosf(fminf(fmaxf(d, -0.999999f), 0.999999f));
+}
+
+__global__ void __launch_bounds__(EE_MAXT, 1) edge_embed_kernel(EdgeEmbedArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int L = a.L;
+  // ---- weights: once per CTA
+  for (int i = tid; i < EE_AA * EE_F; i += T) sm[EE_OFF_WD1 + i] = a.wd1t[i];
+  for (int i = tid; i < EE_F * EE_F; i += T) {
+    sm[EE_OFF_WD2 + i] = a.wd2t[i]; sm[EE_OFF_WO1D + i] = a.wo1dt[i];
+    sm[EE_OFF_WO2 + i] = a.wo2t[i]; sm[EE_OFF_WO3 + i] = a.wo3t[i];
+  }
+  for (int i = tid; i < EE_NH * EE_F; i += T) sm[EE_OFF_WO1H + i] = a.wo1ht[i];
+  for (int i = tid; i < EE_F; i += T) {
+    sm[EE_OFF_B + i] = a.bd1[i]; sm[EE_OFF_B + EE_F + i] = a.bd2[i]; sm[EE_OFF_B + 2 * EE_F + i] = a.bo1[i];
+    sm[EE_OFF_B + 3 * EE_F + i] = a.bo2[i]; sm[EE_OFF_B + 4 * EE_F + i] = a.bo3[i];
+  }
+  for (int i = tid; i < EE_NREL * EE_F; i += T) sm[EE_OFF_TREL + (i >> 6) * EE_TP + (i & 63)] = a.t_rel[i];
+  float* s_c = sm + EE_OFF_C;
+  float* s_taa = sm + EE_OFF_TAA;
+  float* s_pi = sm + EE_OFF_PI;
+  float* s_mi = s_pi + 3 * EE_A;
+  float* s_stage = sm + EE_OFF_STAGE;
+  float* s_pj = s_stage;                      // [T][45]
+  float* s_mj = s_stage + T * 3 * EE_A;       // [T][15]
+
+  for (int row = blockIdx.x; row < a.N * L; row += gridDim.x) {
+    const int b = row / L;
+    const int aai = (int)a.aa[row];
+    const int64_t resi = a.res_nb[row], chi = a.chain_nb[row];
+    const bool smi = a.smask ? (a.smask[row] != 0) : true;
+    __syncthreads();                           // previous row: every thread is done with the per-row tables
+    for (int i = tid; i < EE_NAA * EE_AA; i += T) s_c[i] = a.csp[(size_t)aai * EE_NAA * EE_AA + i];
+    for (int i = tid; i < EE_NAA * EE_F; i += T) s_taa[(i >> 6) * EE_TP + (i & 63)] = a.t_aa[(size_t)aai * EE_NAA * EE_F + i];
+    if (tid < 3 * EE_A) s_pi[tid] = a.pos[(size_t)row * a.A_in * 3 + tid];
+    if (tid < EE_A) s_mi[tid] = a.mask[(size_t)row * a.A_in + tid] ? 1.f : 0.f;
+    for (int j0 = 0; j0 < L; j0 += T) {
+      const int nj = min(T, L - j0);
+      __syncthreads();                         // staging region free (previous pass written out), tables visible
+      for (int i = tid; i < nj * 3 * EE_A; i += T) {
+        const int jl = i / (3 * EE_A), e = i - jl * 3 * EE_A;
+        s_pj[i] = a.pos[((size_t)b * L + j0 + jl) * a.A_in * 3 + e];
+      }
+      for (int i = tid; i < nj * EE_A; i += T) {
+        const int jl = i / EE_A, e = i - jl * EE_A;
+        s_mj[i] = a.mask[((size_t)b * L + j0 + jl) * a.A_in + e] ? 1.f : 0.f;
+      }
+      __syncthreads();
+      const int j = j0 + tid;
+      const bool act = tid < nj;
+      float y[EE_F];
+      if (act) {
+        const size_t rj = (size_t)b * L + j;
+        const int aaj = (int)a.aa[rj];
+        const float psm = (smi && (a.smask ? a.smask[rj] != 0 : true)) ? 1.f : 0.f;
+        const float* pj = s_pj + tid * 3 * EE_A;
+        const float* mj = s_mj + tid * EE_A;
+        const float* crow = s_c + aaj * EE_AA;
+        // ---- distance features -> first distance layer (225 -> 64)
+        float h[EE_F];
+#pragma unroll
+        for (int n = 0; n < EE_F; ++n) h[n] = sm[EE_OFF_B + n];
+        for (int bb = 0; bb < EE_A; ++bb) {
+          const float xj = pj[3 * bb], yj = pj[3 * bb + 1], zj = pj[3 * bb + 2], mjb = mj[bb];
+#pragma unroll 3
+          for (int aa_ = 0; aa_ < EE_A; ++aa_) {
+            const int k = aa_ * EE_A + bb;
+            const float dx = s_pi[3 * aa_] - xj, dy = s_pi[3 * aa_ + 1] - yj, dz = s_pi[3 * aa_ + 2] - zj;
+            const float d2 = (dx * dx + dy * dy + dz * dz) * 0.01f;          // (|.| / 10)^2
+            const float g = __expf(-crow[k] * d2) * (s_mi[aa_] * mjb);
+            ee_axpy64(h, g, sm + EE_OFF_WD1 + k * EE_F);
+          }
+        }
+        // ---- second distance layer (64 -> 64), relu, structure mask
+#pragma unroll
+        for (int n = 0; n < EE_F; ++n) y[n] = sm[EE_OFF_B + EE_F + n];
+#pragma unroll
+        for (int k = 0; k < EE_F; ++k) ee_axpy64(y, fmaxf(h[k], 0.f), sm + EE_OFF_WD2 + k * EE_F);
+        // ---- first output layer: lookups + distance part + dihedral part
+        {
+          int64_t rel = resi - a.res_nb[rj];
+          rel = rel < -32 ? -32 : (rel > 32 ? 32 : rel);
+          const float same = (chi == a.chain_nb[rj]) ? 1.f : 0.f;
+          const float* ta = s_taa + aaj * EE_TP;
+          const float* tr = sm + EE_OFF_TREL + (int)(rel + 32) * EE_TP;
+#pragma unroll
+          for (int n = 0; n < EE_F; ++n) h[n] = sm[EE_OFF_B + 2 * EE_F + n] + ta[n] + same * tr[n];
+        }
+#pragma unroll
+        for (int k = 0; k < EE_F; ++k) ee_axpy64(h, fmaxf(y[k], 0.f) * psm, sm + EE_OFF_WO1D + k * EE_F);
+        {
+          // phi = dihedral(C_i, N_j, CA_j, C_j), psi = dihedral(N_i, CA_i, C_i, N_j); atoms N 0, CA 1, C 2
+          const float ang[2] = {ee_dihedral(s_pi + 6, pj, pj + 3, pj + 6), ee_dihedral(s_pi, s_pi + 3, s_pi + 6, pj)};
+          const float fr[6] = {1.f, 2.f, 3.f, 1.f, 1.f / 2.f, 1.f / 3.f};
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float* w = sm + EE_OFF_WO1H + q * 13 * EE_F;
+            ee_axpy64(h, ang[q] * psm, w);
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+              float sv, cv;
+              sincosf(ang[q] * fr[f], &sv, &cv);
+              ee_axpy64(h, sv * psm, w + (1 + f) * EE_F);
+              ee_axpy64(h, cv * psm, w + (7 + f) * EE_F);
+            }
+          }
+        }
+        // ---- output layers 2 and 3, pair mask
+#pragma unroll
+        for (int n = 0; n < EE_F; ++n) y[n] = sm[EE_OFF_B + 3 * EE_F + n];
+#pragma unroll
+        for (int k = 0; k < EE_F; ++k) ee_axpy64(y, fmaxf(h[k], 0.f), sm + EE_OFF_WO2 + k * EE_F);
+#pragma unroll
+        for (int n = 0; n < EE_F; ++n) h[n] = sm[EE_OFF_B + 4 * EE_F + n];
+#pragma unroll
+        for (int k = 0; k < EE_F; ++k) ee_axpy64(h, fmaxf(y[k], 0.f), sm + EE_OFF_WO3 + k * EE_F);
+        const float mp = s_mi[1] * mj[1];                                    // CA masks of both residues
+#pragma unroll
+        for (int n = 0; n < EE_F; ++n) y[n] = h[n] * mp;
+      }
+      __syncthreads();                         // everyone is done reading x_j / m_j: the region becomes the staging tile
+      if (act) {
+#pragma unroll
+        for (int n = 0; n < EE_F; ++n) s_stage[tid * EE_TP + n] = y[n];
+      }
+      __syncthreads();
+      float* dst = a.out + ((size_t)row * L + j0) * EE_F;
+      for (int i = tid; i < nj * EE_F; i += T) dst[i] = s_stage[(i >> 6) * EE_TP + (i & 63)];
+    }
+  }
+}
+
+static size_t edge_embed_smem(int T) { return (size_t)(EE_OFF_STAGE + T * EE_TP) * sizeof(float); }
+
+void embed_kernels_init() {
+  cudaFuncSetAttribute(edge_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_embed_smem(EE_MAXT));
+}
+
+}  // namespace pf
+
+extern "C" int pf_edge_embed(const int64_t* aa, const int64_t* res_nb, const int64_t* chain_nb, const float* pos_atoms,
+                             const uint8_t* mask_atoms, const uint8_t* structure_mask, const float* softplus_coef,
+                             const float* t_aa, const float* t_rel, const float* wd1_t, const float* bd1,
+                             const float* wd2_t, const float* bd2, const float* wo1d_t, const float* wo1h_t,
+                             const float* bo1, const float* wo2_t, const float* bo2, const float* wo3_t,
+                             const float* bo3, float* out, int N, int L, int atoms_in, void* stream) {
+  using namespace pf;
+  PF_REQUIRE(aa && res_nb && chain_nb && pos_atoms && mask_atoms && softplus_coef && t_aa && t_rel && wd1_t && bd1 &&
+                 wd2_t && bd2 && wo1d_t && wo1h_t && bo1 && wo2_t && bo2 && wo3_t && bo3 && out, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(N >= 0 && L >= 0 && atoms_in >= EE_A, PF_ERR_BAD_SHAPE);
+  if (N == 0 || L == 0) return PF_OK;
+  // threads per CTA: the row of L pairs in ceil(L / 256) equal passes, rounded up to whole warps
+  const int passes = (L + EE_MAXT - 1) / EE_MAXT;
+  int T = ((L + passes - 1) / passes + 31) & ~31;
+  if (T < 64) T = 64;
+  EdgeEmbedArgs a{aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, softplus_coef, t_aa, t_rel,
+                  wd1_t, wd2_t, wo1d_t, wo1h_t, wo2_t, wo3_t, bd1, bd2, bo1, bo2, bo3, out, N, L, atoms_in};
+  const long long rows = (long long)N * L;
+  const int grid = (int)(rows < num_sms() ? rows : num_sms());
+  edge_embed_kernel<<<grid, T, edge_embed_smem(T), as_stream(stream)>>>(a);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}

@@ -62,78 +62,62 @@ __device__ __forceinline__ float v2_vprime(const IpaPack2Args& a, size_t row, in
   return 0.f;
 }
 
-__global__ void ipa_pack2_kernel(IpaPack2Args a) {
+// One CTA per key-tile blob (blockIdx.x < B * JT: K' / V' fragments, key bias, key mask of 8 keys, all heads) or
+// per query tile (the remaining B * IT CTAs: Q' fragments of 16 rows, all heads).  All index arithmetic is 32-bit
+// with compile-time divisors; reads touch whole 32-byte sectors, writes are contiguous.
+__global__ void __launch_bounds__(256) ipa_pack2_kernel(IpaPack2Args a) {
   const int L = a.L;
-  const size_t nK = (size_t)a.B * a.JT * H * V2_KS * 32;
-  const size_t nV = (size_t)a.B * a.JT * H * V2_VNT * 32;
-  const size_t nB = (size_t)a.B * a.JT * (H + 1) * V2_TK;
-  const size_t nQ = (size_t)a.B * H * a.IT * V2_KS * 32;
-  size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (idx < nK) {
-    const int lane = idx & 31;
-    size_t r = idx >> 5;
-    const int ks = r % V2_KS; r /= V2_KS;
-    const int h = r % H; r /= H;
-    const int jt = r % a.JT, b = (int)(r / a.JT);
-    const int g = lane >> 2, t = lane & 3, j = jt * V2_TK + g;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (j < L) {
-      const size_t row = (size_t)b * L + j;
-      const int kk = ks * 16 + 2 * t;
-      v[0] = v2_kprime(a, row, h, kk); v[1] = v2_kprime(a, row, h, kk + 1);
-      v[2] = v2_kprime(a, row, h, kk + 8); v[3] = v2_kprime(a, row, h, kk + 9);
-    }
-    uint4 o;
-    split_pair(v[0], v[1], o.x, o.z);
-    split_pair(v[2], v[3], o.y, o.w);
-    unsigned char* blob = a.blobs + ((size_t)b * a.JT + jt) * V2_BLOB;
-    reinterpret_cast<uint4*>(blob)[(h * V2_KS + ks) * 32 + lane] = o;
-    return;
-  }
-  idx -= nK;
-  if (idx < nV) {
-    const int lane = idx & 31;
-    size_t r = idx >> 5;
-    const int nt = r % V2_VNT; r /= V2_VNT;
-    const int h = r % H; r /= H;
-    const int jt = r % a.JT, b = (int)(r / a.JT);
-    const int g = lane >> 2, t = lane & 3, n = nt * 8 + g, j = jt * V2_TK + 2 * t;
-    const float v0 = (j < L) ? v2_vprime(a, (size_t)b * L + j, h, n) : 0.f;
-    const float v1 = (j + 1 < L) ? v2_vprime(a, (size_t)b * L + j + 1, h, n) : 0.f;
-    uint2 o;
-    split_pair(v0, v1, o.x, o.y);
-    unsigned char* blob = a.blobs + ((size_t)b * a.JT + jt) * V2_BLOB + V2_OFF_V;
-    reinterpret_cast<uint2*>(blob)[(h * V2_VNT + nt) * 32 + lane] = o;
-    return;
-  }
-  idx -= nV;
-  if (idx < nB) {
-    const int key = idx % V2_TK;
-    size_t r = idx / V2_TK;
-    const int h = r % (H + 1); r /= (H + 1);
-    const int jt = r % a.JT, b = (int)(r / a.JT);
-    const int j = jt * V2_TK + key;
-    float* dst = reinterpret_cast<float*>(a.blobs + ((size_t)b * a.JT + jt) * V2_BLOB + V2_OFF_KB);
-    if (h == H) {
-      dst[H * V2_TK + key] = (j < L) ? a.mask[(size_t)b * L + j] : 0.f;
-    } else {
-      float s = 0.f;
+  const int nblob = a.B * a.JT;
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < nblob) {
+    const int b = blockIdx.x / a.JT, jt = blockIdx.x - b * a.JT;
+    const size_t row0 = (size_t)b * L;
+    unsigned char* blob = a.blobs + (size_t)blockIdx.x * V2_BLOB;
+    for (int idx = tid; idx < H * V2_KS * 32; idx += 256) {           // K' [h][ks][lane]
+      const int lane = idx & 31, r = idx >> 5, ks = r % V2_KS, h = r / V2_KS;
+      const int g = lane >> 2, t = lane & 3, j = jt * V2_TK + g;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (j < L) {
-        const float* kp = a.pts + (((size_t)b * L + j) * H + h) * (NPT * 3) + PQ * 3;
-#pragma unroll
-        for (int e = 0; e < PQ * 3; ++e) s = fmaf(kp[e], kp[e], s);
+        const int kk = ks * 16 + 2 * t;
+        v[0] = v2_kprime(a, row0 + j, h, kk); v[1] = v2_kprime(a, row0 + j, h, kk + 1);
+        v[2] = v2_kprime(a, row0 + j, h, kk + 8); v[3] = v2_kprime(a, row0 + j, h, kk + 9);
       }
-      dst[h * V2_TK + key] = -0.5f * a.head_w[h] * s;
+      uint4 o;
+      split_pair(v[0], v[1], o.x, o.z);
+      split_pair(v[2], v[3], o.y, o.w);
+      reinterpret_cast<uint4*>(blob)[idx] = o;
+    }
+    for (int idx = tid; idx < H * V2_VNT * 32; idx += 256) {          // V' [h][nt][lane]
+      const int lane = idx & 31, r = idx >> 5, nt = r % V2_VNT, h = r / V2_VNT;
+      const int g = lane >> 2, t = lane & 3, n = nt * 8 + g, j = jt * V2_TK + 2 * t;
+      const float v0 = (j < L) ? v2_vprime(a, row0 + j, h, n) : 0.f;
+      const float v1 = (j + 1 < L) ? v2_vprime(a, row0 + j + 1, h, n) : 0.f;
+      uint2 o;
+      split_pair(v0, v1, o.x, o.y);
+      reinterpret_cast<uint2*>(blob + V2_OFF_V)[idx] = o;
+    }
+    if (tid < (H + 1) * V2_TK) {                                       // key bias [h][key], key mask [key]
+      const int key = tid % V2_TK, h = tid / V2_TK, j = jt * V2_TK + key;
+      float* dst = reinterpret_cast<float*>(blob + V2_OFF_KB);
+      if (h == H) {
+        dst[H * V2_TK + key] = (j < L) ? a.mask[row0 + j] : 0.f;
+      } else {
+        float s = 0.f;
+        if (j < L) {
+          const float* kp = a.pts + ((row0 + j) * H + h) * (NPT * 3) + PQ * 3;
+#pragma unroll
+          for (int e = 0; e < PQ * 3; ++e) s = fmaf(kp[e], kp[e], s);
+        }
+        dst[h * V2_TK + key] = -0.5f * a.head_w[h] * s;
+      }
     }
     return;
   }
-  idx -= nB;
-  if (idx < nQ) {
-    const int lane = idx & 31;
-    size_t r = idx >> 5;
-    const int ks = r % V2_KS; r /= V2_KS;
-    const int it = r % a.IT; r /= a.IT;
-    const int h = r % H, b = (int)(r / H);
+  const int qi = blockIdx.x - nblob;                                   // Q' [b][h][it][ks][lane]{hi, lo}
+  const int b = qi / a.IT, it = qi - b * a.IT;
+  const size_t row0 = (size_t)b * L;
+  for (int idx = tid; idx < H * V2_KS * 32; idx += 256) {
+    const int lane = idx & 31, r = idx >> 5, ks = r % V2_KS, h = r / V2_KS;
     const int g = lane >> 2, t = lane & 3;
     const float ch = a.head_w[h];
     float v[8];
@@ -143,10 +127,9 @@ __global__ void ipa_pack2_kernel(IpaPack2Args a) {
     for (int half = 0; half < 2; ++half) {
       const int i = it * V2_TQ + g + half * 8;
       if (i < L) {
-        const size_t row = (size_t)b * L + i;
         const int kk = ks * 16 + 2 * t;
-        v[half * 2 + 0] = v2_qprime(a, row, h, kk, ch); v[half * 2 + 1] = v2_qprime(a, row, h, kk + 1, ch);
-        v[4 + half * 2 + 0] = v2_qprime(a, row, h, kk + 8, ch); v[4 + half * 2 + 1] = v2_qprime(a, row, h, kk + 9, ch);
+        v[half * 2 + 0] = v2_qprime(a, row0 + i, h, kk, ch); v[half * 2 + 1] = v2_qprime(a, row0 + i, h, kk + 1, ch);
+        v[4 + half * 2 + 0] = v2_qprime(a, row0 + i, h, kk + 8, ch); v[4 + half * 2 + 1] = v2_qprime(a, row0 + i, h, kk + 9, ch);
       }
     }
     uint4 hi, lo;
@@ -510,22 +493,45 @@ size_t ipa_v2_workspace_bytes(int B, int L) {
 constexpr int V3_THREADS = 512;
 constexpr int V3_ZSTAGE_W = 4096;                              // one pair warp, one stage: [2 rows][2 halves] TMA boxes
                                                                // of [8 keys][32 ch] (1 KB, 128-byte swizzle)
-constexpr int V3_SM_BLOB = 0;                                  // 84256
-constexpr int V3_SM_Z = (V3_SM_BLOB + V2_BLOB + 1023) & ~1023; // [8 warps][2 stages][4096]
-constexpr int V3_SM_QLO = V3_SM_Z + 8 * 2 * V3_ZSTAGE_W;       // [8 h][10 ks][32 lanes] uint4
-constexpr int V3_SM_WB = V3_SM_QLO + H * V2_KS * 32 * 16;      // [4 ks][32 lanes] uint4 {hi b0, hi b1, lo b0, lo b1}
-constexpr int V3_SM_BIAS = V3_SM_WB + 4 * 32 * 16;             // [2][8 h][16 i][10]
-constexpr int V3_SM_P = V3_SM_BIAS + 2 * H * V2_TQ * V2_BP * 4;   // [2][16 i][68]
-constexpr int V3_SM_ALPHA = V3_SM_P + 2 * V2_TQ * V2_PP * 4;   // [2][8 h][16 i]
-constexpr int V3_SM_L = V3_SM_ALPHA + 2 * H * V2_TQ * 4;       // [8 h][16 i]
-constexpr int V3_SM_BAR = V3_SM_L + H * V2_TQ * 4;             // 4 blob mbarriers + [8 warps][2 stages] z mbarriers
-constexpr int V3_SMEM = V3_SM_BAR + 32 + 128;
-static_assert(V3_SM_Z % 1024 == 0 && V3_SM_QLO % 16 == 0 && V3_SM_P % 16 == 0 && V3_SM_BAR % 8 == 0, "alignment");
-static_assert(V3_SMEM <= 232448, "shared memory budget");
-// epilogue re-use of the loop buffers
-static_assert(V2_TQ * H * CZ * 4 <= V2_BLOB, "o_pair_raw fits in the blob region");
-static_assert(H * V2_TQ * 40 * 4 <= 8 * 2 * V3_ZSTAGE_W, "o_pt scratch fits in the z region");
+// shared-memory layout; DEC = decoupled pair-warp pipeline (variant 4): V4_SLOTS row slots of 2 KB per pair warp
+// (one mbarrier each) instead of 2 stages of 2 rows, paid for by moving the Q' lo fragments to tensor memory
+constexpr int V4_SLOTS = 6;
+#ifndef V4_HEAD_REGS
+#define V4_HEAD_REGS 152
+#endif
+constexpr int V3_PH = 68;            // uint2 per head in a P tile (64 used; pitch = 8 words mod 32)
+template <bool DEC>
+struct V3L {
+  static constexpr int ZWARP = DEC ? V4_SLOTS * 2048 : 2 * V3_ZSTAGE_W;  // z bytes owned by one pair warp
+  static constexpr int NZBAR = DEC ? V4_SLOTS : 2;                 // z mbarriers per pair warp
+  static constexpr int SM_BLOB = 0;                                // 84256
+  static constexpr int SM_Z = (SM_BLOB + V2_BLOB + 1023) & ~1023;  // [8 warps][ZWARP]
+  static constexpr int SM_QLO = SM_Z + 8 * ZWARP;                  // [8 h][10 ks][32 lanes] uint4 (not DEC)
+  static constexpr int SM_WB = SM_QLO + (DEC ? 0 : H * V2_KS * 32 * 16);   // [4 ks][32 lanes] uint4 {hi b0, hi b1, lo b0, lo b1}
+  static constexpr int SM_BIAS = SM_WB + 4 * 32 * 16;              // [2][8 h][16 i][10]
+  static constexpr int SM_P = SM_BIAS + 2 * H * V2_TQ * V2_BP * 4; // [2][8 h][V3_PH] uint2 {P hi, P lo}: [16 i][4 key pairs] + pad
+  static constexpr int SM_ALPHA = SM_P + 2 * H * V3_PH * 8;        // [2][8 h][16 i]
+  static constexpr int SM_L = SM_ALPHA + 2 * H * V2_TQ * 4;        // [8 h][16 i]
+  static constexpr int SM_BAR = SM_L + H * V2_TQ * 4;              // 4 blob mbarriers + [8 warps][NZBAR] z mbarriers
+  static constexpr int SM_TMEM = SM_BAR + 32 + 8 * NZBAR * 8;      // tensor-memory base address (DEC)
+  static constexpr int SMEM = SM_TMEM + 16;
+  // epilogue staging of W_dz [16 d][68]: the Q' lo region, or (DEC) the z region behind the o_pt scratch
+  static constexpr int SM_WDZ = DEC ? SM_Z + H * V2_TQ * 40 * 4 : SM_QLO;
+  static_assert(!DEC || H * V2_TQ * 40 * 4 + 16 * V2_ZP * 4 <= 8 * ZWARP, "W_dz staging fits behind the o_pt scratch");
+  static_assert(SM_Z % 1024 == 0 && SM_QLO % 16 == 0 && SM_P % 16 == 0 && SM_BAR % 8 == 0, "alignment");
+  static_assert(SMEM <= 232448, "shared memory budget");
+  // epilogue re-use of the loop buffers
+  static_assert(V2_TQ * H * V2_ZP * 4 <= V2_BLOB, "o_pair_raw fits in the blob region");
+  static_assert(H * V2_TQ * 40 * 4 <= 8 * ZWARP, "o_pt scratch fits in the z region");
+};
 
+// four 8x8 b16 matrices, transposed on the way in; lane l supplies the address of row l & 7 of matrix l >> 3
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr)
+               : "memory");
+}
 __device__ __forceinline__ void named_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
 }
@@ -543,15 +549,17 @@ __device__ __forceinline__ int v3_zoff(int r, int key, int c) {
   return ((r * 2 + (c >> 5)) << 10) + (key << 7) + ((((c & 31) >> 2) ^ key) << 4) + ((c & 3) << 2);
 }
 
+template <bool DEC>
 __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const __grid_constant__ Ipa3Args args) {
+  using LT = V3L<DEC>;
   const Ipa2Args& p = args.p;
   extern __shared__ __align__(128) unsigned char smem[];
-  const unsigned char* blob = smem + V3_SM_BLOB;
-  float* sbias = reinterpret_cast<float*>(smem + V3_SM_BIAS);
-  float* sP = reinterpret_cast<float*>(smem + V3_SM_P);
-  float* salpha = reinterpret_cast<float*>(smem + V3_SM_ALPHA);
-  float* sl = reinterpret_cast<float*>(smem + V3_SM_L);
-  const uint32_t bar_kfull = smem_u32(smem + V3_SM_BAR), bar_vfull = bar_kfull + 8, bar_kfree = bar_kfull + 16,
+  const unsigned char* blob = smem + LT::SM_BLOB;
+  float* sbias = reinterpret_cast<float*>(smem + LT::SM_BIAS);
+  uint2* sP = reinterpret_cast<uint2*>(smem + LT::SM_P);
+  float* salpha = reinterpret_cast<float*>(smem + LT::SM_ALPHA);
+  float* sl = reinterpret_cast<float*>(smem + LT::SM_L);
+  const uint32_t bar_kfull = smem_u32(smem + LT::SM_BAR), bar_vfull = bar_kfull + 8, bar_kfree = bar_kfull + 16,
                  bar_vfree = bar_kfull + 24;
   const IpaArgs& a = p.a;
   const int L = a.L, JT = p.JT;
@@ -566,38 +574,65 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
     mbar_init(bar_vfull, 1);
     mbar_init(bar_kfree, 8);
     mbar_init(bar_vfree, 8);
-    for (int q = 0; q < 16; ++q) mbar_init(bar_kfull + 32 + 8 * q, 1);
+    for (int q = 0; q < 8 * LT::NZBAR; ++q) mbar_init(bar_kfull + 32 + 8 * q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     tma_prefetch_desc(&args.tm_z);
   }
   // W_b as B fragments of the pair-bias MMA (rows n = head, k = channel; sqrt(1/3) folded in)
   if (tid < 128) {
     const int ks = tid >> 5, gg = (tid & 31) >> 2, tt = tid & 3;
-    const float* w = a.w_b + gg * CZ + ks * 16 + 2 * tt;
+    // K slots (2t, 2t+1 | 2t+8, 2t+9) of K step ks carry channels 16 ks + 4t .. 4t+3, so that the matching A
+    // fragment is ONE 16-byte load per pair
+    const float* w = a.w_b + gg * CZ + ks * 16 + 4 * tt;
     uint4 o;
     split_pair(w[0] * sc_b, w[1] * sc_b, o.x, o.z);
-    split_pair(w[8] * sc_b, w[9] * sc_b, o.y, o.w);
-    reinterpret_cast<uint4*>(smem + V3_SM_WB)[tid] = o;
+    split_pair(w[2] * sc_b, w[3] * sc_b, o.y, o.w);
+    reinterpret_cast<uint4*>(smem + LT::SM_WB)[tid] = o;
   }
-  // lo halves of the Q' fragments (the hi halves stay in the head warps' registers)
-  for (int idx = tid; idx < H * V2_KS * 32; idx += V3_THREADS) {
-    const int hh = idx / (V2_KS * 32), rem = idx % (V2_KS * 32);
-    reinterpret_cast<uint4*>(smem + V3_SM_QLO)[idx] =
-        p.Qp[(((size_t)b * H + hh) * p.IT + it) * V2_QTILE_U4 + rem * 2 + 1];
+  // lo halves of the Q' fragments (the hi halves stay in the head warps' registers): shared memory, or (DEC) tensor
+  // memory - 40 columns per head warp, written below by the warp that reads them back
+  if constexpr (!DEC) {
+    for (int idx = tid; idx < H * V2_KS * 32; idx += V3_THREADS) {
+      const int hh = idx / (V2_KS * 32), rem = idx % (V2_KS * 32);
+      reinterpret_cast<uint4*>(smem + LT::SM_QLO)[idx] =
+          p.Qp[(((size_t)b * H + hh) * p.IT + it) * V2_QTILE_U4 + rem * 2 + 1];
+    }
+  } else {
+    if (warp == 0) tmem_alloc_cta(smem_u32(smem + LT::SM_TMEM), 256);
+    tc_fence_before();
   }
   __syncthreads();
+  uint32_t tmem_base = 0;
+  if constexpr (DEC) {
+    tc_fence_after();
+    tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + LT::SM_TMEM);
+  }
 
   if (warp < 8) {
     // ========================================== head warps ======================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;\n");
+    if constexpr (DEC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(V4_HEAD_REGS));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 176;\n");
     const int h = warp;
-    uint4 qh[V2_KS];
+    uint4 qh[DEC ? 1 : V2_KS];                        // Q' hi fragments: registers, or (DEC) tensor memory
+    const uint4* qlo = reinterpret_cast<const uint4*>(smem + LT::SM_QLO) + (h * V2_KS) * 32 + lane;
+    // (DEC) tensor-memory address of this warp's Q' fragments: its own lane quadrant, 80 columns per warp
+    // ([ks]{hi x4, lo x4}), which leaves the head warps 40 registers lighter and the pair warps 104 registers
+    const uint32_t tq = tmem_base + ((32u * (warp & 3)) << 16) + 80u * (warp >> 2);
     {
       const uint4* qp = p.Qp + (((size_t)b * H + h) * p.IT + it) * V2_QTILE_U4;
+      if constexpr (!DEC) {
 #pragma unroll
-      for (int ks = 0; ks < V2_KS; ++ks) qh[ks] = qp[(ks * 32 + lane) * 2];
+        for (int ks = 0; ks < V2_KS; ++ks) qh[ks] = qp[(ks * 32 + lane) * 2];
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < V2_KS; ++ks) {
+          const uint4 hi = qp[(ks * 32 + lane) * 2], lo = qp[(ks * 32 + lane) * 2 + 1];
+          const uint32_t r[8] = {hi.x, hi.y, hi.z, hi.w, lo.x, lo.y, lo.z, lo.w};
+          tmem_st8(tq + 8 * ks, r);
+        }
+        tc_wait_st();
+      }
     }
-    const uint4* qlo = reinterpret_cast<const uint4*>(smem + V3_SM_QLO) + (h * V2_KS) * 32 + lane;
     const float bbias = sc_b * a.b_b[h];
     const float mi_lo = (i0 + g < L) ? a.mask[rowb + i0 + g] : 0.f;
     const float mi_hi = (i0 + g + 8 < L) ? a.mask[rowb + i0 + g + 8] : 0.f;
@@ -608,9 +643,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
     float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
     if (tid == 0) {
       mbar_arrive_expect_tx(bar_kfull, V2_BLOB_HEAD);
-      bulk_g2s(smem_u32(smem + V3_SM_BLOB), gblob, V2_BLOB_HEAD, bar_kfull);
+      bulk_g2s(smem_u32(smem + LT::SM_BLOB), gblob, V2_BLOB_HEAD, bar_kfull);
       mbar_arrive_expect_tx(bar_vfull, V2_BLOB_V);
-      bulk_g2s(smem_u32(smem + V3_SM_BLOB + V2_OFF_V), gblob + V2_OFF_V, V2_BLOB_V, bar_vfull);
+      bulk_g2s(smem_u32(smem + LT::SM_BLOB + V2_OFF_V), gblob + V2_OFF_V, V2_BLOB_V, bar_vfull);
     }
     for (int jt = 0; jt < JT; ++jt) {
       const int j0 = jt * V2_TK, par = jt & 1;
@@ -619,20 +654,41 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
       float S[4];
       float kbv[2], mjv[2];
       {
-        float Sa[4] = {0.f, 0.f, 0.f, 0.f}, Sb[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint4* kp = reinterpret_cast<const uint4*>(blob) + (h * V2_KS) * 32 + lane;
+        float Sc[4][4];                                // four independent accumulation chains (7-8 MMAs each)
 #pragma unroll
-        for (int ks = 0; ks < V2_KS; ++ks) {
-          const uint4 k0 = kp[ks * 32];
-          const uint4 q_lo = qlo[ks * 32];
-          const uint32_t ah[4] = {qh[ks].x, qh[ks].y, qh[ks].z, qh[ks].w};
-          const uint32_t al[4] = {q_lo.x, q_lo.y, q_lo.z, q_lo.w};
-          mma16816(Sa, al, k0.x, k0.y);
-          mma16816(Sb, ah, k0.x, k0.y);
-          mma16816(Sa, ah, k0.z, k0.w);
+        for (int q = 0; q < 4; ++q) { Sc[q][0] = Sc[q][1] = Sc[q][2] = Sc[q][3] = 0.f; }
+        const uint4* kp = reinterpret_cast<const uint4*>(blob) + (h * V2_KS) * 32 + lane;
+        if constexpr (!DEC) {
+#pragma unroll
+          for (int ks = 0; ks < V2_KS; ++ks) {
+            const uint4 k0 = kp[ks * 32];
+            const uint4 q_lo = qlo[ks * 32];
+            const uint32_t ah[4] = {qh[ks].x, qh[ks].y, qh[ks].z, qh[ks].w};
+            const uint32_t al[4] = {q_lo.x, q_lo.y, q_lo.z, q_lo.w};
+            mma16816(Sc[(3 * ks) & 3], al, k0.x, k0.y);
+            mma16816(Sc[(3 * ks + 1) & 3], ah, k0.x, k0.y);
+            mma16816(Sc[(3 * ks + 2) & 3], ah, k0.z, k0.w);
+          }
+        } else {
+          // Q' comes back from tensor memory one K step at a time; the load of the next step is in flight under the
+          // MMAs of this one
+          uint32_t qq[2][8];
+          tmem_ld8(tq, qq[0]);
+          tc_wait_ld();
+#pragma unroll
+          for (int ks = 0; ks < V2_KS; ++ks) {
+            if (ks + 1 < V2_KS) tmem_ld8(tq + 8 * (ks + 1), qq[(ks + 1) & 1]);
+            const uint4 k0 = kp[ks * 32];
+            const uint32_t ah[4] = {qq[ks & 1][0], qq[ks & 1][1], qq[ks & 1][2], qq[ks & 1][3]};
+            const uint32_t al[4] = {qq[ks & 1][4], qq[ks & 1][5], qq[ks & 1][6], qq[ks & 1][7]};
+            mma16816(Sc[(3 * ks) & 3], al, k0.x, k0.y);
+            mma16816(Sc[(3 * ks + 1) & 3], ah, k0.x, k0.y);
+            mma16816(Sc[(3 * ks + 2) & 3], ah, k0.z, k0.w);
+            tc_wait_ld();
+          }
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) S[e] = Sa[e] + Sb[e];
+        for (int e = 0; e < 4; ++e) S[e] = (Sc[0][e] + Sc[1][e]) + (Sc[2][e] + Sc[3][e]);
 #pragma unroll
         for (int e = 0; e < 2; ++e) { kbv[e] = skb[h * V2_TK + 2 * t + e] + bbias; mjv[e] = skb[H * V2_TK + 2 * t + e]; }
       }
@@ -641,11 +697,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
       if (tid == 0 && jt + 1 < JT) {                   // producer: refill the K' part once every head warp is done
         mbar_wait(bar_kfree, par);
         mbar_arrive_expect_tx(bar_kfull, V2_BLOB_HEAD);
-        bulk_g2s(smem_u32(smem + V3_SM_BLOB), gblob + (size_t)(jt + 1) * V2_BLOB, V2_BLOB_HEAD, bar_kfull);
+        bulk_g2s(smem_u32(smem + LT::SM_BLOB), gblob + (size_t)(jt + 1) * V2_BLOB, V2_BLOB_HEAD, bar_kfull);
       }
       __syncwarp();
       // ---- logits and online softmax (row g: S[0..1], row g+8: S[2..3]; keys 2t, 2t+1)
       named_sync(1 + par, V3_THREADS);                 // pair bias of this tile is in sbias[par]
+      uint32_t ph0, pl0, ph1, pl1;
       {
         const float* bs = sbias + par * (H * V2_TQ * V2_BP);
         float mx_lo = -INFINITY, mx_hi = -INFINITY;
@@ -665,19 +722,33 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
         mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
         mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
         mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-        const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
-        const float al_lo = expf(m_lo - mn_lo), al_hi = expf(m_hi - mn_hi);   // exp(-inf) = 0 on the first tile
-        m_lo = mn_lo; m_hi = mn_hi;
+        // Lazy rescale: the running maximum only moves when some row of the warp exceeds it by more than 8
+        // (P <= e^8 stays far inside fp16 / fp32 range); otherwise alpha = 1 and the 84 accumulator multiplies of
+        // this warp - and the pair warps' - are skipped.  The final O / l is unchanged mathematically.
+#ifndef V3_NO_LAZY
+        const bool resc = __any_sync(0xffffffffu, (mx_lo > m_lo + 8.f) || (mx_hi > m_hi + 8.f));
+#else
+        const bool resc = true;
+#endif
+        float al_lo = 1.f, al_hi = 1.f;
+        if (resc) {
+          const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
+          al_lo = expf(m_lo - mn_lo); al_hi = expf(m_hi - mn_hi);             // exp(-inf) = 0 on the first tile
+          m_lo = mn_lo; m_hi = mn_hi;
+        }
         float ps_lo = 0.f, ps_hi = 0.f;
-        float* Pw = sP + par * (V2_TQ * V2_PP);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const float p_lo = expf(S[e] - mn_lo), p_hi = expf(S[2 + e] - mn_hi);
+          const float p_lo = expf(S[e] - m_lo), p_hi = expf(S[2 + e] - m_hi);
           S[e] = p_lo; S[2 + e] = p_hi;
           ps_lo += p_lo; ps_hi += p_hi;
-          const int j = 2 * t + e;
-          Pw[g * V2_PP + j * 8 + h] = p_lo;
-          Pw[(g + 8) * V2_PP + j * 8 + h] = p_hi;
+        }
+        split_pair(S[0], S[1], ph0, pl0);              // a0: row g,   keys 2t, 2t+1
+        split_pair(S[2], S[3], ph1, pl1);              // a1: row g+8
+        {
+          uint2* Pw = sP + (par * H + h) * V3_PH;      // [row][key pair] {hi, lo}: what the pair warps' B fragments hold
+          Pw[g * 4 + t] = make_uint2(ph0, pl0);
+          Pw[(g + 8) * 4 + t] = make_uint2(ph1, pl1);
         }
         l_lo = l_lo * al_lo + ps_lo;
         l_hi = l_hi * al_hi + ps_hi;
@@ -686,22 +757,23 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
           salpha[par * (H * V2_TQ) + h * V2_TQ + g + 8] = al_hi;
         }
         named_arrive(3 + par, V3_THREADS);             // P / alpha of this tile are in sP[par], salpha[par]
+        if (resc) {
 #pragma unroll
-        for (int n = 0; n < V2_VNT; ++n) { O[n][0] *= al_lo; O[n][1] *= al_lo; O[n][2] *= al_hi; O[n][3] *= al_hi; }
+          for (int n = 0; n < V2_VNT; ++n) { O[n][0] *= al_lo; O[n][1] *= al_lo; O[n][2] *= al_hi; O[n][3] *= al_hi; }
+        }
       }
       // ---- O += P [V | v_pts]   (m16n8k8: K = the 8 keys of the tile)
       mbar_wait(bar_vfull, par);
       {
-        uint32_t ph0, pl0, ph1, pl1;
-        split_pair(S[0], S[1], ph0, pl0);              // a0: row g,   keys 2t, 2t+1
-        split_pair(S[2], S[3], ph1, pl1);              // a1: row g+8
+        // HMMA m16n8k8 occupies the tensor pipe as long as m16n8k16 (8 cycles per sub-core, measured with
+        // scripts/ubench/hmma_rate.cu), so two of the three split-precision products share one K = 16 MMA
+        const uint32_t pa[4] = {ph0, ph1, pl0, pl1};
         const uint2* vp = reinterpret_cast<const uint2*>(blob + V2_OFF_V) + (h * V2_VNT) * 32 + lane;
 #pragma unroll
         for (int n = 0; n < V2_VNT; ++n) {
           const uint2 v = vp[n * 32];
-          mma1688(O[n], pl0, pl1, v.x);
-          mma1688(O[n], ph0, ph1, v.y);
-          mma1688(O[n], ph0, ph1, v.x);
+          mma16816(O[n], pa, v.x, v.x);                // K = [P hi | P lo] x [V hi ; V hi]
+          mma1688(O[n], ph0, ph1, v.y);                // P hi x V lo
         }
       }
       __syncwarp();
@@ -709,7 +781,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
       if (tid == 0 && jt + 1 < JT) {
         mbar_wait(bar_vfree, par);
         mbar_arrive_expect_tx(bar_vfull, V2_BLOB_V);
-        bulk_g2s(smem_u32(smem + V3_SM_BLOB + V2_OFF_V), gblob + (size_t)(jt + 1) * V2_BLOB + V2_OFF_V, V2_BLOB_V,
+        bulk_g2s(smem_u32(smem + LT::SM_BLOB + V2_OFF_V), gblob + (size_t)(jt + 1) * V2_BLOB + V2_OFF_V, V2_BLOB_V,
                  bar_vfull);
       }
       __syncwarp();
@@ -720,7 +792,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
     const float il_lo = 1.0f / l_lo, il_hi = 1.0f / l_hi;
     if (t == 0) { sl[h * V2_TQ + g] = il_lo; sl[h * V2_TQ + g + 8] = il_hi; }
     named_sync(5, V3_THREADS);                         // every warp has left the tile loop: z region and blob are free
-    float* spt = reinterpret_cast<float*>(smem + V3_SM_Z);   // [8 h][16 i][40] normalised global-frame o_pt
+    float* spt = reinterpret_cast<float*>(smem + LT::SM_Z);   // [8 h][16 i][40] normalised global-frame o_pt
     const int i_lo = i0 + g, i_hi = i0 + g + 8;
 #pragma unroll
     for (int n = 0; n < 16; ++n) {                     // o: channels 8n + 2t, +1
@@ -742,105 +814,181 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
     asm volatile("setmaxnreg.dec.sync.aligned.u32 128;\n");
   } else {
     // ========================================== pair warps ======================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+    if constexpr (DEC) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(256 - V4_HEAD_REGS));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 80;\n");
     const int pw = warp - 8, r0 = 2 * pw;             // this warp owns query rows r0, r0 + 1
-    const uint32_t zbase = smem_u32(smem + V3_SM_Z + pw * 2 * V3_ZSTAGE_W);   // [2 stages][4096]
-    const unsigned char* zgen = smem + V3_SM_Z + pw * 2 * V3_ZSTAGE_W;
-    const uint32_t zbar = bar_kfull + 32 + 16 * pw;   // + 8 * stage
-    const uint4* wbf = reinterpret_cast<const uint4*>(smem + V3_SM_WB) + lane;
-    auto issue_z = [&](int jt) {                       // one lane: 4 boxes = (2 rows) x (2 channel halves)
-      const int st = jt & 1;
-      mbar_arrive_expect_tx(zbar + 8 * st, V3_ZSTAGE_W);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        tma_load_3d(zbase + st * V3_ZSTAGE_W + q * 1024, &args.tm_z, 32 * (q & 1), jt * V2_TK,
-                    (int)rowb + i0 + r0 + (q >> 1), zbar + 8 * st);
-    };
+    const uint32_t zbase = smem_u32(smem + LT::SM_Z + pw * LT::ZWARP);
+    unsigned char* zgen = smem + LT::SM_Z + pw * LT::ZWARP;
+    const uint32_t zbar = bar_kfull + 32 + 8 * LT::NZBAR * pw;
+    const uint4* wbf = reinterpret_cast<const uint4*>(smem + LT::SM_WB) + lane;
     float acc[2][4][4];   // o_pair_raw^T: [row][m-tile of 16 channels][C fragment: (ch g | g+8) x (heads 2t, 2t+1)]
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) { acc[r][mt][0] = acc[r][mt][1] = acc[r][mt][2] = acc[r][mt][3] = 0.f; }
-    if (lane == 0) issue_z(0);
-    for (int jt = 0; jt < JT; ++jt) {
-      const int par = jt & 1;
-      __syncwarp();                                    // every lane is done with the other stage (tile jt - 1)
-      if (lane == 0 && jt + 1 < JT) issue_z(jt + 1);
-      mbar_wait(zbar + 8 * par, (jt >> 1) & 1);        // z tile jt (this warp's rows) has landed
-      const unsigned char* zt = zgen + par * V3_ZSTAGE_W;
-      // ---- pair bias for rows r0, r0+1 x 8 keys, all heads -> sbias[par]
-      {
-        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+    // ---- pair bias for rows r0 (z tile at za), r0+1 (zb) x 8 keys, all heads -> sbias[par].  The fp16 hi / lo split
+    //      of z that feeds the MMA is also written back IN PLACE: once both K steps of a 32-channel half have been
+    //      read, that 1 KB half of each row ([8 keys][32 ch] fp32) is dead and receives [hi | lo][8 keys][32 ch] fp16
+    //      (16-byte chunks XOR-swizzled by key >> 1), from which the o_pair phase fetches its transposed A
+    //      fragments with ldmatrix.trans instead of re-reading and re-splitting the fp32 tile.
+    //      MMA row g carries key kq = (g >> 1) + 4 (g & 1): the two keys of a quarter-warp then sit in different
+    //      halves of the 128-byte swizzle and every 16-byte load / 8-byte store below is conflict-free.
+    const int kq = (g >> 1) + 4 * (g & 1);
+    const int st_off = kq * 64 + 8 * (t & 1);          // this lane's 8 bytes inside a [8 keys][64 B] fp16 block
+    auto bias_phase = [&](unsigned char* za, unsigned char* zb, int par) {
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const int c = ks * 16 + 2 * t;
-          const float2 x0 = *reinterpret_cast<const float2*>(zt + v3_zoff(0, g, c));       // pair (row r0,   key g)
-          const float2 x1 = *reinterpret_cast<const float2*>(zt + v3_zoff(1, g, c));       // pair (row r0+1, key g)
-          const float2 x2 = *reinterpret_cast<const float2*>(zt + v3_zoff(0, g, c + 8));
-          const float2 x3 = *reinterpret_cast<const float2*>(zt + v3_zoff(1, g, c + 8));
-          uint32_t ah[4], al[4];
-          split_pair(x0.x, x0.y, ah[0], al[0]);
-          split_pair(x1.x, x1.y, ah[1], al[1]);
-          split_pair(x2.x, x2.y, ah[2], al[2]);
-          split_pair(x3.x, x3.y, ah[3], al[3]);
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t hh[2][4], ll[2][4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ks = 2 * hf + e;
+          const int zo = v3_zoff(0, kq, ks * 16 + 4 * t);
+          const float4 xa = *reinterpret_cast<const float4*>(za + zo);        // pair (row r0,   key kq), 4 channels
+          const float4 xb = *reinterpret_cast<const float4*>(zb + zo);        // pair (row r0+1, key kq)
+          split_pair(xa.x, xa.y, hh[e][0], ll[e][0]);
+          split_pair(xb.x, xb.y, hh[e][1], ll[e][1]);
+          split_pair(xa.z, xa.w, hh[e][2], ll[e][2]);
+          split_pair(xb.z, xb.w, hh[e][3], ll[e][3]);
           const uint4 w = wbf[ks * 32];
-          mma16816(c0, al, w.x, w.y);
-          mma16816(c1, ah, w.x, w.y);
-          mma16816(c0, ah, w.z, w.w);
+          mma16816(c0, ll[e], w.x, w.y);
+          mma16816(c1, hh[e], w.x, w.y);
+          mma16816(c0, hh[e], w.z, w.w);
         }
-        float* bs = sbias + par * (H * V2_TQ * V2_BP);
-        bs[((2 * t) * V2_TQ + r0) * V2_BP + g] = c0[0] + c1[0];
-        bs[((2 * t + 1) * V2_TQ + r0) * V2_BP + g] = c0[1] + c1[1];
-        bs[((2 * t) * V2_TQ + r0 + 1) * V2_BP + g] = c0[2] + c1[2];
-        bs[((2 * t + 1) * V2_TQ + r0 + 1) * V2_BP + g] = c0[3] + c1[3];
+        __syncwarp();                                  // every lane has read this half of both rows
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {                  // channels 16 e + 4t .. 4t+3 of the half: 16-byte chunk 2e + (t >> 1)
+          const int sw = (((2 * e + (t >> 1)) ^ (kq >> 1)) & 3) * 16 + st_off + hf * 1024;
+          *reinterpret_cast<uint2*>(za + sw) = make_uint2(hh[e][0], hh[e][2]);
+          *reinterpret_cast<uint2*>(za + sw + 512) = make_uint2(ll[e][0], ll[e][2]);
+          *reinterpret_cast<uint2*>(zb + sw) = make_uint2(hh[e][1], hh[e][3]);
+          *reinterpret_cast<uint2*>(zb + sw + 512) = make_uint2(ll[e][1], ll[e][3]);
+        }
       }
-      named_arrive(1 + par, V3_THREADS);
-      // ---- o_pair_raw^T[c, h] = alpha_h * old + sum_j z[j, c] P[h, j] once the head warps have published P / alpha:
-      //      m16n8k8 with M = 16 channels, N = 8 heads, K = the 8 keys of the tile (3xFP16)
-      named_sync(3 + par, V3_THREADS);
-      {
-        const float* Pr = sP + par * (V2_TQ * V2_PP);
-        const float* al = salpha + par * (H * V2_TQ);
+      float* bs = sbias + par * (H * V2_TQ * V2_BP);
+      bs[((2 * t) * V2_TQ + r0) * V2_BP + kq] = c0[0] + c1[0];
+      bs[((2 * t + 1) * V2_TQ + r0) * V2_BP + kq] = c0[1] + c1[1];
+      bs[((2 * t) * V2_TQ + r0 + 1) * V2_BP + kq] = c0[2] + c1[2];
+      bs[((2 * t + 1) * V2_TQ + r0 + 1) * V2_BP + kq] = c0[3] + c1[3];
+      __syncwarp();                                    // the fp16 copy is complete before any lane's ldmatrix
+    };
+    // ---- o_pair_raw^T[c, h] = alpha_h * old + sum_j z[j, c] P[h, j] for query row r0 + r (fp16 copy of its z tile at
+    //      zr): M = 16 channels, N = 8 heads, K = [z hi | z lo] x [P hi ; P hi] (m16n8k16) + z hi x P lo (m16n8k8).
+    //      ldmatrix.x4.trans: lanes 8m..8m+7 address the key rows of matrix m = {hi ch 0-7, hi ch 8-15, lo ch 0-7,
+    //      lo ch 8-15} of a 16-channel group; transposed, thread (g, t) receives (channel g; keys 2t, 2t+1).
+    const int lm_k = lane & 7, lm_m = lane >> 3;
+    const int lm_base = (lm_m >> 1) * 512 + lm_k * 64;
+    const int lm_even = lm_base + ((((lm_m & 1)) ^ (lm_k >> 1)) & 3) * 16;       // channel groups 0, 2: chunks 0, 1
+    const int lm_odd = lm_base + (((2 + (lm_m & 1)) ^ (lm_k >> 1)) & 3) * 16;    // channel groups 1, 3: chunks 2, 3
+    auto opair_row = [&](const unsigned char* zr, int r, int par) {
+      const uint2 pb = sP[(par * H + g) * V3_PH + (r0 + r) * 4 + t];   // B = P^T: (keys 2t, 2t+1; head g) {hi, lo}
+      const float* al = salpha + par * (H * V2_TQ);
+      const float a0 = al[(2 * t) * V2_TQ + r0 + r], a1 = al[(2 * t + 1) * V2_TQ + r0 + r];
+#ifndef V3_NO_LAZY
+      const bool resc = __any_sync(0xffffffffu, (a0 != 1.f) || (a1 != 1.f));
+#else
+      const bool resc = true;
+#endif
+      const uint32_t zs = smem_u32(zr);
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        uint32_t za[4];                                // {hi ch g, hi ch g+8, lo ch g, lo ch g+8} of channels 16 mt ..
+        ldmatrix_x4_trans(za, zs + (mt >> 1) * 1024 + ((mt & 1) ? lm_odd : lm_even));
+        float (&d)[4] = r == 0 ? acc[0][mt] : acc[1][mt];
+        if (resc) { d[0] *= a0; d[1] *= a1; d[2] *= a0; d[3] *= a1; }
+        mma16816(d, za, pb.x, pb.x);
+        mma1688(d, za[0], za[1], pb.y);
+      }
+    };
+    if constexpr (!DEC) {
+      auto issue_z = [&](int jt) {                       // one lane: 4 boxes = (2 rows) x (2 channel halves)
+        const int st = jt & 1;
+        mbar_arrive_expect_tx(zbar + 8 * st, V3_ZSTAGE_W);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          tma_load_3d(zbase + st * V3_ZSTAGE_W + q * 1024, &args.tm_z, 32 * (q & 1), jt * V2_TK,
+                      (int)rowb + i0 + r0 + (q >> 1), zbar + 8 * st);
+      };
+      if (lane == 0) issue_z(0);
+      for (int jt = 0; jt < JT; ++jt) {
+        const int par = jt & 1;
+        __syncwarp();                                    // every lane is done with the other stage (tile jt - 1)
+        if (lane == 0 && jt + 1 < JT) issue_z(jt + 1);
+        mbar_wait(zbar + 8 * par, (jt >> 1) & 1);        // z tile jt (this warp's rows) has landed
+        unsigned char* zt = zgen + par * V3_ZSTAGE_W;
+        bias_phase(zt, zt + 2048, par);
+        named_arrive(1 + par, V3_THREADS);
+        named_sync(3 + par, V3_THREADS);                 // the head warps have published P / alpha of the tile
+        opair_row(zt, 0, par);
+        opair_row(zt + 2048, 1, par);
+      }
+    } else {
+      // Decoupled pipeline: the bias of tile jt + 1 is computed BEFORE the o_pair accumulation of tile jt, so the
+      // head warps find their bias waiting and the loop-carried chain bias -> softmax -> P -> o_pair -> next bias
+      // is broken.  Row tiles (item n = 2 jt + r, [8 keys][64 ch], 2 KB) cycle through V4_SLOTS = 6 slots: two tiles
+      // resident, one in flight with a full iteration of lead; the slot of an item is refilled with item
+      // n + V4_SLOTS as soon as its o_pair part is done.
+      const int NI = 2 * JT;
+      auto issue_item = [&](int n, int slot) {           // one lane: 2 boxes = 2 channel halves of one query row
+        mbar_arrive_expect_tx(zbar + 8 * slot, 2048);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          tma_load_3d(zbase + slot * 2048 + q * 1024, &args.tm_z, 32 * q, (n >> 1) * V2_TK,
+                      (int)rowb + i0 + r0 + (n & 1), zbar + 8 * slot);
+      };
+      if (lane == 0)
+        for (int n = 0; n < V4_SLOTS && n < NI; ++n) issue_item(n, n);
+      int bslot = 0, bphase = 0;                         // slot / phase of the next item the bias phase consumes
+      int oslot = 0;                                     // slot of the next item the o_pair phase consumes
+      auto next_bias_tile = [&](int par) {
+        const int s0 = bslot, p0 = bphase;
+        bslot = (bslot == V4_SLOTS - 1) ? 0 : bslot + 1; bphase ^= (bslot == 0);
+        const int s1 = bslot, p1 = bphase;
+        bslot = (bslot == V4_SLOTS - 1) ? 0 : bslot + 1; bphase ^= (bslot == 0);
+        mbar_wait(zbar + 8 * s0, p0);
+        mbar_wait(zbar + 8 * s1, p1);
+        bias_phase(zgen + s0 * 2048, zgen + s1 * 2048, par);
+        named_arrive(1 + par, V3_THREADS);
+      };
+      next_bias_tile(0);
+      for (int jt = 0; jt < JT; ++jt) {
+        const int par = jt & 1;
+        if (jt + 1 < JT) next_bias_tile(par ^ 1);
+        named_sync(3 + par, V3_THREADS);                 // the head warps have published P / alpha of the tile
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const float a0 = al[(2 * t) * V2_TQ + r0 + r], a1 = al[(2 * t + 1) * V2_TQ + r0 + r];
-          uint32_t bh, bl;                              // B = P^T: (keys 2t, 2t+1; head g)
-          split_pair(Pr[(r0 + r) * V2_PP + (2 * t) * 8 + g], Pr[(r0 + r) * V2_PP + (2 * t + 1) * 8 + g], bh, bl);
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            const int cA = 16 * mt + g, cB = cA + 8;
-            const float zAA = *reinterpret_cast<const float*>(zt + v3_zoff(r, 2 * t, cA));
-            const float zBA = *reinterpret_cast<const float*>(zt + v3_zoff(r, 2 * t + 1, cA));
-            const float zAB = *reinterpret_cast<const float*>(zt + v3_zoff(r, 2 * t, cB));
-            const float zBB = *reinterpret_cast<const float*>(zt + v3_zoff(r, 2 * t + 1, cB));
-            uint32_t ah0, al0, ah1, al1;
-            split_pair(zAA, zBA, ah0, al0);             // a0: (channel cA; keys 2t, 2t+1)
-            split_pair(zAB, zBB, ah1, al1);             // a1: (channel cB; keys 2t, 2t+1)
-            acc[r][mt][0] *= a0; acc[r][mt][1] *= a1; acc[r][mt][2] *= a0; acc[r][mt][3] *= a1;
-            mma1688(acc[r][mt], al0, al1, bh);
-            mma1688(acc[r][mt], ah0, ah1, bl);
-            mma1688(acc[r][mt], ah0, ah1, bh);
-          }
+          opair_row(zgen + oslot * 2048, r, par);
+          __syncwarp();                                  // every lane is done with the slot
+          const int n = 2 * jt + r + V4_SLOTS;
+          if (lane == 0 && n < NI) issue_item(n, oslot);
+          oslot = (oslot == V4_SLOTS - 1) ? 0 : oslot + 1;
         }
       }
     }
     named_sync(5, V3_THREADS);                         // every warp has left the tile loop: the blob region is free
-    float* sop = reinterpret_cast<float*>(smem + V3_SM_BLOB);   // [16 i][8 h][64]
+    float* sop = reinterpret_cast<float*>(smem + LT::SM_BLOB);   // [16 i][8 h][68]: padded rows, conflict-free both ways
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
-        float* o = sop + ((r0 + r) * H + 2 * t) * CZ + 16 * mt + g;
-        o[0] = acc[r][mt][0]; o[CZ] = acc[r][mt][1];
-        o[8] = acc[r][mt][2]; o[CZ + 8] = acc[r][mt][3];
+        float* o = sop + ((r0 + r) * H + 2 * t) * V2_ZP + 16 * mt + g;
+        o[0] = acc[r][mt][0]; o[V2_ZP] = acc[r][mt][1];
+        o[8] = acc[r][mt][2]; o[V2_ZP + 8] = acc[r][mt][3];
       }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 128;\n");
   }
+  if constexpr (DEC) tc_fence_before();
   __syncthreads();
+  if constexpr (DEC) {
+    if (warp == 0) {
+      tc_fence_after();
+      tmem_dealloc_cta(tmem_base, 256);
+    }
+  }
 
   // ---- common epilogue (all 16 warps)
-  const float* spt = reinterpret_cast<const float*>(smem + V3_SM_Z);
-  const float* sop = reinterpret_cast<const float*>(smem + V3_SM_BLOB);
+  const float* spt = reinterpret_cast<const float*>(smem + LT::SM_Z);
+  const float* sop = reinterpret_cast<const float*>(smem + LT::SM_BLOB);
   // o_pt: global -> local frame, norms (ipa_pytorch.py:455-460)
   for (int idx = tid; idx < H * V2_TQ * PV; idx += V3_THREADS) {
     const int pnt = idx % PV, i = (idx / PV) % V2_TQ, hh = idx / (PV * V2_TQ);
@@ -859,14 +1007,14 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
     f[3 * 96 + hh * PV + pnt] = sqrtf(lx * lx + ly * ly + lz * lz + 1e-8f);
   }
   // o_pair: down_z on the normalised a-weighted pair row (ipa_pytorch.py:469-473); W_dz staged in shared memory
-  float* swz = reinterpret_cast<float*>(smem + V3_SM_QLO);      // [16 d][68]
+  float* swz = reinterpret_cast<float*>(smem + LT::SM_WDZ);      // [16 d][68]
   for (int idx = tid; idx < 16 * CZ; idx += V3_THREADS) swz[(idx >> 6) * V2_ZP + (idx & 63)] = a.w_dz[idx];
   __syncthreads();
   {
     const int pairidx = tid >> 2, d0 = (tid & 3) * 4;   // pairidx = i * 8 + head; 4 of the 16 outputs per thread
     const int i = pairidx >> 3, hh = pairidx & 7;
     if (i0 + i < L) {
-      const float* src = sop + (i * H + hh) * CZ;
+      const float* src = sop + (i * H + hh) * V2_ZP;
       float acc4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
       for (int c = 0; c < CZ; c += 4) {
@@ -889,22 +1037,22 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
   }
 }
 
-int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                            bool decoupled) {
   if (a.B == 0 || a.L == 0) return PF_OK;
   PF_REQUIRE(workspace && workspace_bytes >= ipa_v2_workspace_bytes(a.B, a.L), PF_ERR_WORKSPACE_TOO_SMALL);
   const int JT = (a.L + V2_TK - 1) / V2_TK, IT = (a.L + V2_TQ - 1) / V2_TQ;
   unsigned char* blobs = static_cast<unsigned char*>(workspace);
   uint4* Qp = reinterpret_cast<uint4*>(blobs + (size_t)a.B * JT * V2_BLOB);
   IpaPack2Args pa{a.proj, a.pts, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT};
-  const size_t total = (size_t)a.B * JT * H * V2_KS * 32 + (size_t)a.B * JT * H * V2_VNT * 32 +
-                       (size_t)a.B * JT * (H + 1) * V2_TK + (size_t)a.B * H * IT * V2_KS * 32;
-  ipa_pack2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pa);
+  ipa_pack2_kernel<<<(unsigned)(a.B * JT + a.B * IT), 256, 0, st>>>(pa);
   PF_CHECK_LAUNCH();
   Ipa3Args args;
   PF_TRY(encode_z_map(&args.tm_z, a.z, a.B, a.L));
   args.p = Ipa2Args{a, blobs, Qp, JT, IT};
   profile_begin(0, st);
-  ipa_attention_v3_kernel<<<dim3(IT, a.B), V3_THREADS, V3_SMEM, st>>>(args);
+  if (decoupled) ipa_attention_v3_kernel<true><<<dim3(IT, a.B), V3_THREADS, V3L<true>::SMEM, st>>>(args);
+  else ipa_attention_v3_kernel<false><<<dim3(IT, a.B), V3_THREADS, V3L<false>::SMEM, st>>>(args);
   profile_end(0, st);
   PF_CHECK_LAUNCH();
   return PF_OK;
@@ -917,9 +1065,7 @@ int launch_ipa_attention_v2(const IpaArgs& a, void* workspace, size_t workspace_
   unsigned char* blobs = static_cast<unsigned char*>(workspace);
   uint4* Qp = reinterpret_cast<uint4*>(blobs + (size_t)a.B * JT * V2_BLOB);
   IpaPack2Args pa{a.proj, a.pts, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT};
-  const size_t total = (size_t)a.B * JT * H * V2_KS * 32 + (size_t)a.B * JT * H * V2_VNT * 32 +
-                       (size_t)a.B * JT * (H + 1) * V2_TK + (size_t)a.B * H * IT * V2_KS * 32;
-  ipa_pack2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pa);
+  ipa_pack2_kernel<<<(unsigned)(a.B * JT + a.B * IT), 256, 0, st>>>(pa);
   PF_CHECK_LAUNCH();
   Ipa2Args p{a, blobs, Qp, JT, IT};
   profile_begin(0, st);
@@ -931,7 +1077,8 @@ int launch_ipa_attention_v2(const IpaArgs& a, void* workspace, size_t workspace_
 
 void ipa_v2_kernels_init() {
   cudaFuncSetAttribute(ipa_attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM);
-  cudaFuncSetAttribute(ipa_attention_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
+  cudaFuncSetAttribute(ipa_attention_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3L<false>::SMEM);
+  cudaFuncSetAttribute(ipa_attention_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3L<true>::SMEM);
 }
 
 }  // namespace pf

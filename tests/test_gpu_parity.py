@@ -33,9 +33,9 @@ def model(dev, state_dict):
     return m.to(dev)
 
 
-@pytest.fixture(params=[(0, 0, 0), (2, 2, 3), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1), (0, 0, 2), (0, 0, 3)],
+@pytest.fixture(params=[(0, 0, 0), (2, 2, 4), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4)],
                 ids=["fp32", "tc", "edge_mma_sync", "edge_tcgen05", "gemm_mma_sync", "gemm_tcgen05", "ipa_tc_v1",
-                     "ipa_tc_v2", "ipa_tc_v3"])
+                     "ipa_tc_v2", "ipa_tc_v3", "ipa_tc_v4"])
 def impl(request):
     from pepflowww_b200 import _lib
     edge, gemm, ipa = request.param
@@ -45,7 +45,7 @@ def impl(request):
     yield request.param
     _lib.set_option("edge_impl", 2)
     _lib.set_option("gemm_impl", 2)
-    _lib.set_option("ipa_impl", 3)
+    _lib.set_option("ipa_impl", 4)
 
 
 def cu(g, dev, keys):
