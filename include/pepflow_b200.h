@@ -56,7 +56,7 @@ int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_poin
  *                3 = the same arithmetic, warp-specialised (head warps / pair warps, TMA z ring),
  *                4 = variant 3 with the pair warps decoupled (default): the pair bias of the next key tile is
  *                    computed before the o_pair accumulation of the current one (6-slot z row ring), Q' fragments
- *                    parked in tensor memory so the pair warps get 104 registers                            */
+ *                    parked in tensor memory so the pair warps get 88 registers                            */
 int pf_set_option(const char* name, int value);
 int pf_get_option(const char* name);
 /* Launch counter: number of kernels this library has enqueued since the last reset. */
@@ -207,6 +207,21 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
                           const float* edge_embed, const float* res_mask, float* pred_rot, float* pred_trans,
                           float* pred_angles, float* logits, float* node_out, void* workspace,
                           size_t workspace_bytes, int B, int L, void* stream);
+
+/* ---- once-per-sample pair embedder -------------------------------------------
+ * EdgeEmbedder.forward, models_con/edge.py:39-112, fused: atom coordinates -> [N, L, L, 64] pair features in one
+ * kernel.  aa[N,L] i64 (UNK already substituted where the sequence is hidden, edge.py:66-68), res_nb / chain_nb
+ * [N,L] i64, pos_atoms[N,L,atoms_in,3] fp32 and mask_atoms[N,L,atoms_in] u8 (first 15 atoms used, edge.py:56-57),
+ * structure_mask[N,L] u8 or NULL.  Host-prepared constants: softplus_coef[484,225] = softplus(aapair_to_distcoef);
+ * t_aa[484,64] = aa_pair_embed W_o1[:, 0:64]^T; t_rel[65,64] = relpos_embed W_o1[:, 64:128]^T; the remaining
+ * matrices TRANSPOSED to [in, out]: wd1_t[225,64], wd2_t[64,64] (distance_embed), wo1d_t[64,64] = W_o1[:, 128:192]^T,
+ * wo1h_t[26,64] = W_o1[:, 192:218]^T, wo2_t, wo3_t [64,64] (out_mlp); biases [64].  out[N,L,L,64].            */
+int pf_edge_embed(const int64_t* aa, const int64_t* res_nb, const int64_t* chain_nb, const float* pos_atoms,
+                  const uint8_t* mask_atoms, const uint8_t* structure_mask, const float* softplus_coef,
+                  const float* t_aa, const float* t_rel, const float* wd1_t, const float* bd1, const float* wd2_t,
+                  const float* bd2, const float* wo1d_t, const float* wo1h_t, const float* bo1, const float* wo2_t,
+                  const float* bo2, const float* wo3_t, const float* bo3, float* out, int N, int L, int atoms_in,
+                  void* stream);
 
 #ifdef __cplusplus
 }

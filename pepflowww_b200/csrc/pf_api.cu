@@ -187,6 +187,7 @@ int pf_init(int device) {
   pf::ipa_v2_kernels_init();
   pf::edge_kernels_init();
   pf::gemm_umma_init();
+  pf::embed_kernels_init();
   e = cudaGetLastError();
   return e == cudaSuccess ? PF_OK : static_cast<int>(e);
 }

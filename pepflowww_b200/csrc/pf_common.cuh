@@ -149,5 +149,6 @@ int launch_edge_umma_pack_weights(const float* w1, const float* w2, const float*
 void node_kernels_init();
 void ipa_kernels_init();
 void edge_kernels_init();
+void embed_kernels_init();
 
 }  // namespace pf

@@ -26,7 +26,7 @@ constexpr int EE_F = 64;                        // feature width
 constexpr int EE_NH = 26;                       // dihedral encoding width: 2 angles x (1 + 6 sin + 6 cos)
 constexpr int EE_NAA = 22;                      // amino-acid slots
 constexpr int EE_NREL = 65;                     // relative positions -32..32
-constexpr int EE_MAXT = 256;                    // threads per CTA (pairs per pass), upper bound
+constexpr int EE_MAXT = 192;                    // threads per CTA (pairs per pass), upper bound
 constexpr int EE_TP = EE_F + 1;                 // padded row of the per-pair-type tables and the output staging
 
 // shared-memory layout (floats)
@@ -42,6 +42,7 @@ constexpr int EE_OFF_C = EE_OFF_TREL + EE_NREL * EE_TP;        // [22][225]   so
 constexpr int EE_OFF_TAA = EE_OFF_C + EE_NAA * EE_AA;          // [22][65]    T_aa rows of (aa_i, *)
 constexpr int EE_OFF_PI = EE_OFF_TAA + EE_NAA * EE_TP;         // [45] x_i, [15] m_i, 4 spare
 constexpr int EE_OFF_STAGE = EE_OFF_PI + 64;                   // [T][65] output staging; aliases x_j [T][45], m_j [T][15]
+static_assert((EE_OFF_STAGE + EE_MAXT * EE_TP) * 4 <= 232448, "shared memory budget");
 
 struct EdgeEmbedArgs {
   const int64_t* aa;        // [N, L] (already UNK where the sequence is hidden)
@@ -234,7 +235,7 @@ extern "C" int pf_edge_embed(const int64_t* aa, const int64_t* res_nb, const int
                  wd2_t && bd2 && wo1d_t && wo1h_t && bo1 && wo2_t && bo2 && wo3_t && bo3 && out, PF_ERR_NULL_POINTER);
   PF_REQUIRE(N >= 0 && L >= 0 && atoms_in >= EE_A, PF_ERR_BAD_SHAPE);
   if (N == 0 || L == 0) return PF_OK;
-  // threads per CTA: the row of L pairs in ceil(L / 256) equal passes, rounded up to whole warps
+  // threads per CTA: the row of L pairs in ceil(L / 192) equal passes, rounded up to whole warps
   const int passes = (L + EE_MAXT - 1) / EE_MAXT;
   int T = ((L + passes - 1) / passes + 31) & ~31;
   if (T < 64) T = 64;

@@ -497,23 +497,29 @@ constexpr int V3_ZSTAGE_W = 4096;                              // one pair warp,
 // (one mbarrier each) instead of 2 stages of 2 rows, paid for by moving the Q' lo fragments to tensor memory
 constexpr int V4_SLOTS = 6;
 #ifndef V4_HEAD_REGS
-#define V4_HEAD_REGS 152
+#define V4_HEAD_REGS 168
 #endif
+// Every head warp owns the K' / V' slice of its head: it waits on its own mbarrier and refills the slice itself as
+// soon as IT is done with it - no CTA-wide free / full hand-off, the eight warps drift freely.
+constexpr int V3_KH = V2_KS * 32 * 16 + V2_TK * 4 + V2_TK * 4;   // 5184: K' fragments | key bias [8] | key mask [8]
+constexpr int V3_VH = V2_VNT * 32 * 8;                            // 5376: V' fragments
 constexpr int V3_PH = 68;            // uint2 per head in a P tile (64 used; pitch = 8 words mod 32)
 template <bool DEC>
 struct V3L {
   static constexpr int ZWARP = DEC ? V4_SLOTS * 2048 : 2 * V3_ZSTAGE_W;  // z bytes owned by one pair warp
   static constexpr int NZBAR = DEC ? V4_SLOTS : 2;                 // z mbarriers per pair warp
-  static constexpr int SM_BLOB = 0;                                // 84256
-  static constexpr int SM_Z = (SM_BLOB + V2_BLOB + 1023) & ~1023;  // [8 warps][ZWARP]
+  static constexpr int SM_BLOB = 0;                                // [8 h][V3_KH] K' slices, then [8 h][V3_VH] V' slices
+  static constexpr int SM_VB = SM_BLOB + H * V3_KH;
+  static constexpr int SM_Z = (SM_VB + H * V3_VH + 1023) & ~1023;  // [8 warps][ZWARP]
   static constexpr int SM_QLO = SM_Z + 8 * ZWARP;                  // [8 h][10 ks][32 lanes] uint4 (not DEC)
   static constexpr int SM_WB = SM_QLO + (DEC ? 0 : H * V2_KS * 32 * 16);   // [4 ks][32 lanes] uint4 {hi b0, hi b1, lo b0, lo b1}
   static constexpr int SM_BIAS = SM_WB + 4 * 32 * 16;              // [2][8 h][16 i][10]
   static constexpr int SM_P = SM_BIAS + 2 * H * V2_TQ * V2_BP * 4; // [2][8 h][V3_PH] uint2 {P hi, P lo}: [16 i][4 key pairs] + pad
   static constexpr int SM_ALPHA = SM_P + 2 * H * V3_PH * 8;        // [2][8 h][16 i]
   static constexpr int SM_L = SM_ALPHA + 2 * H * V2_TQ * 4;        // [8 h][16 i]
-  static constexpr int SM_BAR = SM_L + H * V2_TQ * 4;              // 4 blob mbarriers + [8 warps][NZBAR] z mbarriers
-  static constexpr int SM_TMEM = SM_BAR + 32 + 8 * NZBAR * 8;      // tensor-memory base address (DEC)
+  static constexpr int SM_BAR = SM_L + H * V2_TQ * 4;              // K' full [8 h], V' full [8 h], [8 warps][NZBAR] z mbarriers
+  static constexpr int SM_HBAR = SM_BAR + 128 + 8 * NZBAR * 8;     // bias-ready [2] and P-ready [2] mbarriers
+  static constexpr int SM_TMEM = SM_HBAR + 32;                     // tensor-memory base address (DEC)
   static constexpr int SMEM = SM_TMEM + 16;
   // epilogue staging of W_dz [16 d][68]: the Q' lo region, or (DEC) the z region behind the o_pt scratch
   static constexpr int SM_WDZ = DEC ? SM_Z + H * V2_TQ * 40 * 4 : SM_QLO;
@@ -521,7 +527,7 @@ struct V3L {
   static_assert(SM_Z % 1024 == 0 && SM_QLO % 16 == 0 && SM_P % 16 == 0 && SM_BAR % 8 == 0, "alignment");
   static_assert(SMEM <= 232448, "shared memory budget");
   // epilogue re-use of the loop buffers
-  static_assert(V2_TQ * H * V2_ZP * 4 <= V2_BLOB, "o_pair_raw fits in the blob region");
+  static_assert(V2_TQ * H * V2_ZP * 4 <= H * (V3_KH + V3_VH), "o_pair_raw fits in the blob region");
   static_assert(H * V2_TQ * 40 * 4 <= 8 * ZWARP, "o_pt scratch fits in the z region");
 };
 
@@ -559,8 +565,10 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
   uint2* sP = reinterpret_cast<uint2*>(smem + LT::SM_P);
   float* salpha = reinterpret_cast<float*>(smem + LT::SM_ALPHA);
   float* sl = reinterpret_cast<float*>(smem + LT::SM_L);
-  const uint32_t bar_kfull = smem_u32(smem + LT::SM_BAR), bar_vfull = bar_kfull + 8, bar_kfree = bar_kfull + 16,
-                 bar_vfree = bar_kfull + 24;
+  const uint32_t bar_kfull = smem_u32(smem + LT::SM_BAR), bar_vfull = bar_kfull + 64;   // [8 h] each
+  // hand-offs between the warp groups: per-tile-parity mbarriers instead of CTA-wide named barriers, so the eight head
+  // warps are not forced into lockstep (one warp's softmax runs under another's MMAs)
+  const uint32_t bar_bias = smem_u32(smem + LT::SM_HBAR), bar_p = bar_bias + 16;
   const IpaArgs& a = p.a;
   const int L = a.L, JT = p.JT;
   const int b = blockIdx.y, it = blockIdx.x, i0 = it * V2_TQ;
@@ -570,11 +578,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
   const unsigned char* gblob = p.blobs + (size_t)b * JT * V2_BLOB;
 
   if (tid == 0) {
-    mbar_init(bar_kfull, 1);
-    mbar_init(bar_vfull, 1);
-    mbar_init(bar_kfree, 8);
-    mbar_init(bar_vfree, 8);
-    for (int q = 0; q < 8 * LT::NZBAR; ++q) mbar_init(bar_kfull + 32 + 8 * q, 1);
+    for (int q = 0; q < 16; ++q) mbar_init(bar_kfull + 8 * q, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(bar_bias + 8 * q, 8);   // one arrival per producing warp
+    for (int q = 0; q < 8 * LT::NZBAR; ++q) mbar_init(bar_kfull + 128 + 8 * q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     tma_prefetch_desc(&args.tm_z);
   }
@@ -636,28 +642,38 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
     const float bbias = sc_b * a.b_b[h];
     const float mi_lo = (i0 + g < L) ? a.mask[rowb + i0 + g] : 0.f;
     const float mi_hi = (i0 + g + 8 < L) ? a.mask[rowb + i0 + g + 8] : 0.f;
-    const float* skb = reinterpret_cast<const float*>(blob + V2_OFF_KB);   // [h][8] then mask [8]
+    const unsigned char* kmine = smem + LT::SM_BLOB + h * V3_KH;
+    const unsigned char* vmine = smem + LT::SM_VB + h * V3_VH;
+    const float* skb = reinterpret_cast<const float*>(kmine + V2_KS * 32 * 16);   // key bias [8] then key mask [8]
+    const uint32_t my_kfull = bar_kfull + 8 * h, my_vfull = bar_vfull + 8 * h;
+    auto issue_k = [&](int jt) {                       // one lane: this head's K' fragments, key bias, key mask
+      const unsigned char* src = gblob + (size_t)jt * V2_BLOB;
+      const uint32_t dst = smem_u32(kmine);
+      mbar_arrive_expect_tx(my_kfull, V3_KH);
+      bulk_g2s(dst, src + h * (V2_KS * 32 * 16), V2_KS * 32 * 16, my_kfull);
+      bulk_g2s(dst + V2_KS * 32 * 16, src + V2_OFF_KB + h * (V2_TK * 4), V2_TK * 4, my_kfull);
+      bulk_g2s(dst + V2_KS * 32 * 16 + V2_TK * 4, src + V2_OFF_M, V2_TK * 4, my_kfull);
+    };
+    auto issue_v = [&](int jt) {
+      mbar_arrive_expect_tx(my_vfull, V3_VH);
+      bulk_g2s(smem_u32(vmine), gblob + (size_t)jt * V2_BLOB + V2_OFF_V + h * V3_VH, V3_VH, my_vfull);
+    };
     float O[V2_VNT][4];
 #pragma unroll
     for (int n = 0; n < V2_VNT; ++n) { O[n][0] = O[n][1] = O[n][2] = O[n][3] = 0.f; }
     float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
-    if (tid == 0) {
-      mbar_arrive_expect_tx(bar_kfull, V2_BLOB_HEAD);
-      bulk_g2s(smem_u32(smem + LT::SM_BLOB), gblob, V2_BLOB_HEAD, bar_kfull);
-      mbar_arrive_expect_tx(bar_vfull, V2_BLOB_V);
-      bulk_g2s(smem_u32(smem + LT::SM_BLOB + V2_OFF_V), gblob + V2_OFF_V, V2_BLOB_V, bar_vfull);
-    }
+    if (lane == 0) { issue_k(0); issue_v(0); }
     for (int jt = 0; jt < JT; ++jt) {
       const int j0 = jt * V2_TK, par = jt & 1;
       // ---- S = Q' K'^T (16 rows x 8 keys)
-      mbar_wait(bar_kfull, par);
+      mbar_wait_cta(my_kfull, par);
       float S[4];
       float kbv[2], mjv[2];
       {
         float Sc[4][4];                                // four independent accumulation chains (7-8 MMAs each)
 #pragma unroll
         for (int q = 0; q < 4; ++q) { Sc[q][0] = Sc[q][1] = Sc[q][2] = Sc[q][3] = 0.f; }
-        const uint4* kp = reinterpret_cast<const uint4*>(blob) + (h * V2_KS) * 32 + lane;
+        const uint4* kp = reinterpret_cast<const uint4*>(kmine) + lane;
         if constexpr (!DEC) {
 #pragma unroll
           for (int ks = 0; ks < V2_KS; ++ks) {
@@ -690,18 +706,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
 #pragma unroll
         for (int e = 0; e < 4; ++e) S[e] = (Sc[0][e] + Sc[1][e]) + (Sc[2][e] + Sc[3][e]);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) { kbv[e] = skb[h * V2_TK + 2 * t + e] + bbias; mjv[e] = skb[H * V2_TK + 2 * t + e]; }
+        for (int e = 0; e < 2; ++e) { kbv[e] = skb[2 * t + e] + bbias; mjv[e] = skb[V2_TK + 2 * t + e]; }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_kfree);          // this warp is done with K' / key bias / mask of the tile
-      if (tid == 0 && jt + 1 < JT) {                   // producer: refill the K' part once every head warp is done
-        mbar_wait(bar_kfree, par);
-        mbar_arrive_expect_tx(bar_kfull, V2_BLOB_HEAD);
-        bulk_g2s(smem_u32(smem + LT::SM_BLOB), gblob + (size_t)(jt + 1) * V2_BLOB, V2_BLOB_HEAD, bar_kfull);
-      }
-      __syncwarp();
+      __syncwarp();                                    // this warp is done with its K' / key bias / mask of the tile
+      if (lane == 0 && jt + 1 < JT) issue_k(jt + 1);
       // ---- logits and online softmax (row g: S[0..1], row g+8: S[2..3]; keys 2t, 2t+1)
-      named_sync(1 + par, V3_THREADS);                 // pair bias of this tile is in sbias[par]
+      mbar_wait_cta(bar_bias + 8 * par, (jt >> 1) & 1);    // pair bias of this tile is in sbias[par]
       uint32_t ph0, pl0, ph1, pl1;
       {
         const float* bs = sbias + par * (H * V2_TQ * V2_BP);
@@ -756,19 +766,20 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
           salpha[par * (H * V2_TQ) + h * V2_TQ + g] = al_lo;
           salpha[par * (H * V2_TQ) + h * V2_TQ + g + 8] = al_hi;
         }
-        named_arrive(3 + par, V3_THREADS);             // P / alpha of this tile are in sP[par], salpha[par]
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p + 8 * par);   // P / alpha of this tile are in sP[par], salpha[par]
         if (resc) {
 #pragma unroll
           for (int n = 0; n < V2_VNT; ++n) { O[n][0] *= al_lo; O[n][1] *= al_lo; O[n][2] *= al_hi; O[n][3] *= al_hi; }
         }
       }
       // ---- O += P [V | v_pts]   (m16n8k8: K = the 8 keys of the tile)
-      mbar_wait(bar_vfull, par);
+      mbar_wait_cta(my_vfull, par);
       {
         // HMMA m16n8k8 occupies the tensor pipe as long as m16n8k16 (8 cycles per sub-core, measured with
         // scripts/ubench/hmma_rate.cu), so two of the three split-precision products share one K = 16 MMA
         const uint32_t pa[4] = {ph0, ph1, pl0, pl1};
-        const uint2* vp = reinterpret_cast<const uint2*>(blob + V2_OFF_V) + (h * V2_VNT) * 32 + lane;
+        const uint2* vp = reinterpret_cast<const uint2*>(vmine) + lane;
 #pragma unroll
         for (int n = 0; n < V2_VNT; ++n) {
           const uint2 v = vp[n * 32];
@@ -777,14 +788,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_vfree);
-      if (tid == 0 && jt + 1 < JT) {
-        mbar_wait(bar_vfree, par);
-        mbar_arrive_expect_tx(bar_vfull, V2_BLOB_V);
-        bulk_g2s(smem_u32(smem + LT::SM_BLOB + V2_OFF_V), gblob + (size_t)(jt + 1) * V2_BLOB + V2_OFF_V, V2_BLOB_V,
-                 bar_vfull);
-      }
-      __syncwarp();
+      if (lane == 0 && jt + 1 < JT) issue_v(jt + 1);
     }
     // ---- head epilogue: normalise, write o, stage o_pt
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
@@ -819,7 +823,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
     const int pw = warp - 8, r0 = 2 * pw;             // this warp owns query rows r0, r0 + 1
     const uint32_t zbase = smem_u32(smem + LT::SM_Z + pw * LT::ZWARP);
     unsigned char* zgen = smem + LT::SM_Z + pw * LT::ZWARP;
-    const uint32_t zbar = bar_kfull + 32 + 8 * LT::NZBAR * pw;
+    const uint32_t zbar = bar_kfull + 128 + 8 * LT::NZBAR * pw;
     const uint4* wbf = reinterpret_cast<const uint4*>(smem + LT::SM_WB) + lane;
     float acc[2][4][4];   // o_pair_raw^T: [row][m-tile of 16 channels][C fragment: (ch g | g+8) x (heads 2t, 2t+1)]
 #pragma unroll
@@ -914,11 +918,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
         const int par = jt & 1;
         __syncwarp();                                    // every lane is done with the other stage (tile jt - 1)
         if (lane == 0 && jt + 1 < JT) issue_z(jt + 1);
-        mbar_wait(zbar + 8 * par, (jt >> 1) & 1);        // z tile jt (this warp's rows) has landed
+        mbar_wait_cta(zbar + 8 * par, (jt >> 1) & 1);        // z tile jt (this warp's rows) has landed
         unsigned char* zt = zgen + par * V3_ZSTAGE_W;
         bias_phase(zt, zt + 2048, par);
-        named_arrive(1 + par, V3_THREADS);
-        named_sync(3 + par, V3_THREADS);                 // the head warps have published P / alpha of the tile
+        if (lane == 0) mbar_arrive(bar_bias + 8 * par);
+        mbar_wait_cta(bar_p + 8 * par, (jt >> 1) & 1);       // the head warps have published P / alpha of the tile
         opair_row(zt, 0, par);
         opair_row(zt + 2048, 1, par);
       }
@@ -945,16 +949,16 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
         bslot = (bslot == V4_SLOTS - 1) ? 0 : bslot + 1; bphase ^= (bslot == 0);
         const int s1 = bslot, p1 = bphase;
         bslot = (bslot == V4_SLOTS - 1) ? 0 : bslot + 1; bphase ^= (bslot == 0);
-        mbar_wait(zbar + 8 * s0, p0);
-        mbar_wait(zbar + 8 * s1, p1);
+        mbar_wait_cta(zbar + 8 * s0, p0);
+        mbar_wait_cta(zbar + 8 * s1, p1);
         bias_phase(zgen + s0 * 2048, zgen + s1 * 2048, par);
-        named_arrive(1 + par, V3_THREADS);
+        if (lane == 0) mbar_arrive(bar_bias + 8 * par);
       };
       next_bias_tile(0);
       for (int jt = 0; jt < JT; ++jt) {
         const int par = jt & 1;
         if (jt + 1 < JT) next_bias_tile(par ^ 1);
-        named_sync(3 + par, V3_THREADS);                 // the head warps have published P / alpha of the tile
+        mbar_wait_cta(bar_p + 8 * par, (jt >> 1) & 1);       // the head warps have published P / alpha of the tile
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           opair_row(zgen + oslot * 2048, r, par);

@@ -80,6 +80,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// CTA-scope variant for kernels without a cluster: the .cluster acquire above makes ptxas emit CCTL.IVALL (an L1
+// invalidate) after every successful wait
+__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+
 // plain local arrive / arrive announcing `bytes` of bulk-copy traffic that will complete on this barrier
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");

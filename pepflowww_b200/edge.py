@@ -1,7 +1,9 @@
 """EdgeEmbedder (reference: models_con/edge.py:15-112): once per sample; same parameter names/shapes.
-PyTorch ops on the batch's device - SURVEY section 8(f) rank 1 ("next" row), not the per-step hot path.
-The pair dimension is processed in row chunks so the [B,L,L,225] distance features never exceed
-`chunk_bytes` (the reference materialises them ~5x, 21 GB transient at B=64, L=271)."""
+SURVEY section 8(f) rank 1.  On a CUDA device without autograd (sampling) the whole module is ONE fused kernel
+(pf_edge_embed, csrc/pf_embed.cu): atom coordinates -> [B,L,L,64] pair features, nothing of size L^2 x 225 in HBM.
+With autograd (training) or on CPU tensors the reference formulation below runs as torch ops, the pair dimension
+processed in row chunks so the [B,L,L,225] distance features never exceed `chunk_bytes` (the reference
+materialises them ~5x, 21 GB transient at B=64, L=271)."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -53,9 +55,28 @@ class EdgeEmbedder(nn.Module):
         out = self.out_mlp(torch.cat([f_aa, f_rel, f_d, f_h], dim=-1))
         return out * (mask_residue[:, sl, None] * mask_residue[:, None, :])[..., None]
 
+    def _kernel_constants(self):
+        """Constants of pf_edge_embed in prototype order: softplus(coef), the two embedding tables pushed through the
+        first output layer, transposed weights, biases."""
+        F_ = self.aa_pair_embed.weight.shape[1]
+        d0, d2 = self.distance_embed[0], self.distance_embed[2]
+        o0, o2, o4 = self.out_mlp[0], self.out_mlp[2], self.out_mlp[4]
+        w = o0.weight
+        return (F.softplus(self.aapair_to_distcoef.weight), self.aa_pair_embed.weight @ w[:, :F_].t(),
+                self.relpos_embed.weight @ w[:, F_:2 * F_].t(), d0.weight.t().contiguous(), d0.bias,
+                d2.weight.t().contiguous(), d2.bias, w[:, 2 * F_:3 * F_].t().contiguous(), w[:, 3 * F_:].t().contiguous(),
+                o0.bias, o2.weight.t().contiguous(), o2.bias, o4.weight.t().contiguous(), o4.bias)
+
     def forward(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask=None, sequence_mask=None):
         N, L = aa.size()
         A = self.max_num_atoms
+        fused = (pos_atoms.is_cuda and not torch.is_grad_enabled() and A == 15 and self.max_aa_types == 22 and
+                 self.max_relpos == 32 and self.aa_pair_embed.weight.shape[1] == 64 and self.dihedral_embed.num_funcs == 3)
+        if fused:
+            from . import ops
+            if sequence_mask is not None:
+                aa = torch.where(sequence_mask, aa, torch.full_like(aa, fill_value=int(AA.UNK)))
+            return ops.edge_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, self._kernel_constants())
         pos_atoms, mask_atoms = pos_atoms[:, :, :A], mask_atoms[:, :, :A]
         mask_residue = mask_atoms[:, :, BBHeavyAtom.CA]
         if sequence_mask is not None:

@@ -218,3 +218,19 @@ def ga_encoder_forward(weights_struct, t, rot_t, trans_t, angles_t, seqs_t, node
                                     ptr(node_out, allow_none=True), ptr(workspace, U8), workspace.numel(), B, L,
                                     stream()))
     return out
+
+
+def edge_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, consts):
+    """EdgeEmbedder.forward (models_con/edge.py:39-112) as one fused kernel (pf_edge_embed).  `consts` is the tuple of
+    host-prepared constants in the order of the C prototype (EdgeEmbedder._kernel_constants)."""
+    lib = _lib.lib_for(pos_atoms.device)
+    N, L = aa.shape
+    pos = _c(pos_atoms)
+    m = _c(mask_atoms, torch.bool).view(U8)
+    sm = _c(structure_mask, torch.bool).view(U8) if structure_mask is not None else None
+    out = torch.empty(N, L, L, 64, device=pos.device, dtype=F32)
+    cs = [_c(c) for c in consts]
+    check(lib.pf_edge_embed(ptr(_c(aa, I64), I64), ptr(_c(res_nb, I64), I64), ptr(_c(chain_nb, I64), I64), ptr(pos),
+                            ptr(m, U8), ptr(sm, U8, allow_none=True), *[ptr(c) for c in cs], ptr(out), N, L,
+                            pos.shape[2], stream()))
+    return out

@@ -423,6 +423,63 @@ def test_embedders_on_gpu(dev, model):
     print("embedder gpu-vs-cpu: node %.2e edge %.2e" % (rel_err(enc[4].cpu(), g["node_embed"]), rel_err(enc[5].cpu(), g["edge_embed"])))
 
 
+def _well_conditioned_pairs(pos, margin=0.05):
+    """Pairs whose inter-residue dihedrals (geometry.py:393-418) stay `margin` rad away from 0 and pi: the reference
+    takes acos() of a clamped cosine, whose derivative 1 / sin(theta) amplifies fp32 rounding without bound there."""
+    from oracle import pepflow_oracle as orc
+    N, L = pos.shape[:2]
+    pN, pCA, pC = pos[:, :, 0], pos[:, :, 1], pos[:, :, 2]
+    ex = lambda x, dim: x.unsqueeze(dim).expand(N, L, L, 3)
+    phi = orc.dihedral(ex(pC, 2), ex(pN, 1), ex(pCA, 1), ex(pC, 1)).abs()
+    psi = orc.dihedral(ex(pN, 2), ex(pCA, 2), ex(pC, 2), ex(pN, 1)).abs()
+    ok = lambda a: (a > margin) & (a < math.pi - margin)
+    return ok(phi) & ok(psi)
+
+
+def test_edge_embed_kernel(dev, model, state_dict):
+    """pf_edge_embed (fused EdgeEmbedder) against the reference's output (golden fixture),
+    against the oracle on a padded batch (masked residues, hidden sequence / structure) and - at the bench residue
+    count, two passes per row - against the torch formulation of the same module.  1e-4 relative to the largest
+    feature on every pair whose dihedrals are well conditioned; 2e-3 on the rest (acos near +-1, the bound the
+    torch-GPU-vs-reference comparison of the same module needs as well)."""
+    from oracle import pepflow_oracle as orc
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    from pepflowww_b200.utils import recursive_to
+    keys = ("aa", "res_nb", "chain_nb", "pos_heavyatom", "mask_heavyatom")
+
+    def errs(out, ref, pos):
+        ok = _well_conditioned_pairs(pos.cpu())
+        scale = float(ref.abs().max())
+        d = (out.cpu() - ref.cpu()).abs().amax(-1)
+        return float(d[ok].max()) / scale, float(d.max()) / scale, float(ok.float().mean())
+
+    g = load_golden("encode")
+    ctx = g["mask_heavyatom"][:, :, 1] & ~g["generate_mask"]
+    with torch.no_grad():
+        out = model.edge_embedder(*[g[k].to(dev) for k in keys], structure_mask=ctx.to(dev), sequence_mask=ctx.to(dev))
+    res = {"golden": errs(out, g["edge_embed"], g["pos_heavyatom"])}
+    batch = synthetic_batch(3, 20, 5, seed=11, eight=True)            # L = 25 padded to 32: masked rows / columns
+    ctx = batch["mask_heavyatom"][:, :, 1] & ~batch["generate_mask"]
+    with torch.no_grad():
+        out = model.edge_embedder(*[batch[k].to(dev) for k in keys], structure_mask=ctx.to(dev), sequence_mask=ctx.to(dev))
+        out_nomask = model.edge_embedder(*[batch[k].to(dev) for k in keys])
+    res["padded"] = errs(out, orc.edge_embedder(state_dict, *[batch[k] for k in keys], ctx, ctx), batch["pos_heavyatom"])
+    res["no-mask"] = errs(out_nomask, orc.edge_embedder(state_dict, *[batch[k] for k in keys], None, None),
+                          batch["pos_heavyatom"])
+    assert (out.cpu()[~batch["res_mask"]] == 0).all()
+    big = recursive_to(synthetic_batch(2, 256, 15, seed=4), dev)     # L = 271: two passes over a row
+    ctx = big["mask_heavyatom"][:, :, 1] & ~big["generate_mask"]
+    with torch.no_grad():
+        fused = model.edge_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx)
+    with torch.enable_grad():                                          # autograd on: the torch formulation runs
+        torch_path = model.edge_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx).detach()
+    res["L=271 vs torch ops"] = errs(fused, torch_path, big["pos_heavyatom"])
+    print("edge_embed kernel (well-conditioned pairs, all pairs, share well-conditioned): " +
+          "; ".join("%s %.2e %.2e %.2f" % ((k,) + v) for k, v in res.items()))
+    for k, (e_ok, e_all, share) in res.items():
+        assert e_ok < TOL and e_all < 2e-3 and share > 0.5, (k, e_ok, e_all, share)
+
+
 def test_sample_free_running_flags_and_shapes(dev, model):
     from pepflowww_b200.pep_dataloader import synthetic_batch
     from pepflowww_b200.utils import recursive_to
