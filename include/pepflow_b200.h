@@ -56,7 +56,11 @@ int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_poin
  *                3 = the same arithmetic, warp-specialised (head warps / pair warps, TMA z ring),
  *                4 = variant 3 with the pair warps decoupled (default): the pair bias of the next key tile is
  *                    computed before the o_pair accumulation of the current one (6-slot z row ring), Q' fragments
- *                    parked in tensor memory so the pair warps get 88 registers                            */
+ *                    parked in tensor memory so the pair warps get 88 registers
+ *   "chain_impl": 1 = the K = 128 node layers between the attention kernels run as fused layer chains (one
+ *                kernel per chain, activations in tensor memory; needs gemm_impl = 2 and prepacked weights;
+ *                default), 0 = one GEMM / LayerNorm launch per layer
+ */
 int pf_set_option(const char* name, int value);
 int pf_get_option(const char* name);
 /* Launch counter: number of kernels this library has enqueued since the last reset. */

@@ -12,7 +12,7 @@ namespace pf {
 
 static std::atomic<int64_t> g_launches{0};
 static int g_num_sms = 148;
-static std::atomic<int> g_edge_impl{2}, g_gemm_impl{2}, g_ipa_impl{4};
+static std::atomic<int> g_edge_impl{2}, g_gemm_impl{2}, g_ipa_impl{4}, g_chain_impl{1};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -50,6 +50,7 @@ void* debug_buffer(size_t bytes) { return g_dbg_bytes.load() >= bytes ? g_dbg_pt
 int opt_edge_impl() { return g_edge_impl.load(std::memory_order_relaxed); }
 int opt_gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
 int opt_ipa_impl() { return g_ipa_impl.load(std::memory_order_relaxed); }
+int opt_chain_impl() { return g_chain_impl.load(std::memory_order_relaxed); }
 
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -120,6 +121,7 @@ static size_t enumerate_packables(const pf_ga_weights* w, std::vector<PackItem>*
       lin(W[o], 384); lin(W[o + 2], 128); lin(W[o + 4], 128); lin(W[o + 6], 128);
     }
     lin(W[PF_B_NT1_W], 128); lin(W[PF_B_NT2_W], 128); lin(W[PF_B_NT3_W], 128);
+    lin(W[PF_B_POST_W], 128); lin(W[PF_B_BB_W], 6);
     if (W[PF_B_ET_W1] && W[PF_B_ET_W2] && W[PF_B_ET_WF]) {
       if (items) items->push_back(PackItem{W[PF_B_ET_W1], 0, off, true, W[PF_B_ET_W2], W[PF_B_ET_WF]});
       off += al(edge_umma_weight_image_bytes());
@@ -204,6 +206,7 @@ int pf_set_option(const char* name, int value) {
   if (!std::strcmp(name, "edge_impl") && (value >= 0 && value <= 2)) { pf::g_edge_impl = value; return PF_OK; }
   if (!std::strcmp(name, "gemm_impl") && (value >= 0 && value <= 2)) { pf::g_gemm_impl = value; return PF_OK; }
   if (!std::strcmp(name, "ipa_impl") && (value >= 0 && value <= 4)) { pf::g_ipa_impl = value; return PF_OK; }
+  if (!std::strcmp(name, "chain_impl") && (value >= 0 && value <= 1)) { pf::g_chain_impl = value; return PF_OK; }
   return PF_ERR_BAD_OPTION;
 }
 
@@ -212,6 +215,7 @@ int pf_get_option(const char* name) {
   if (!std::strcmp(name, "edge_impl")) return pf::opt_edge_impl();
   if (!std::strcmp(name, "gemm_impl")) return pf::opt_gemm_impl();
   if (!std::strcmp(name, "ipa_impl")) return pf::opt_ipa_impl();
+  if (!std::strcmp(name, "chain_impl")) return pf::opt_chain_impl();
   return PF_ERR_BAD_OPTION;
 }
 
@@ -296,7 +300,34 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
   PF_TRY(launch_mix_features(node_embed, w->g[PF_G_SEQ_EMB], seqs_t, t, w->g[PF_G_TIME_FREQS], angles_t,
                              w->g[PF_G_ANG_FREQS], ws.xmix, B, L, st));
   PF_TRY(launch_linear(ws.xmix, w->g[PF_G_MIX0_W], w->g[PF_G_MIX0_B], nullptr, nullptr, ws.ta, M, NMIX, 128, 1, st));
-  PF_TRY(launch_linear(ws.ta, w->g[PF_G_MIX2_W], w->g[PF_G_MIX2_B], nullptr, res_mask, ws.s, M, 128, 128, 0, st));
+  // Fused layer chains (chain_impl = 1): need the tcgen05 GEMM and the prepacked weight images of every layer
+  const bool chains = opt_chain_impl() == 1 && opt_gemm_impl() == 2 && !packed.empty();
+  auto stage = [&](const float* wt, const float* bias, int N, int act) {
+    NodeChainStage c{};
+    c.wpack = find_packed(wt, false); c.bias = bias; c.N = N; c.act = act;
+    return c;
+  };
+  auto run_chain = [&](const float* x0, std::vector<NodeChainStage>& c) -> int {
+    for (const NodeChainStage& q : c) PF_REQUIRE(q.wpack, PF_ERR_BAD_CONFIG);
+    return launch_node_chain(x0, M, c.data(), (int)c.size(), st);
+  };
+  auto proj_stage = [&](int b) {
+    NodeChainStage c = stage(w->blk[b][PF_B_PROJ_W], w->blk[b][PF_B_PROJ_B], NPROJ, 0);
+    c.out = ws.proj;
+    return c;
+  };
+  if (chains) {
+    // mix2 (+ mask) -> s, then block 0's IPA projection from the same rows
+    std::vector<NodeChainStage> c;
+    NodeChainStage m2 = stage(w->g[PF_G_MIX2_W], w->g[PF_G_MIX2_B], 128, 0);
+    m2.rowmask = res_mask; m2.out = ws.s; m2.next_a = true;
+    c.push_back(m2);
+    PF_REQUIRE(w->blk[0][PF_B_PROJ_W], PF_ERR_NULL_POINTER);
+    c.push_back(proj_stage(0));
+    PF_TRY(run_chain(ws.ta, c));
+  } else {
+    PF_TRY(launch_linear(ws.ta, w->g[PF_G_MIX2_W], w->g[PF_G_MIX2_B], nullptr, res_mask, ws.s, M, 128, 128, 0, st));
+  }
 
   const float* rot = rot_t;      // block 0 uses the input rotation matrices as they are (ga.py:96)
   const float* trans = trans_t;
@@ -306,38 +337,91 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
     const float* const* W = w->blk[b];
     const int n_need = (b < nb - 1) ? PF_B_NSLOTS : PF_B_ET_INIT_W;
     for (int i = 0; i < n_need; ++i) PF_REQUIRE(W[i], PF_ERR_NULL_POINTER);
-    // IPA (ga.py:98-104)
-    PF_TRY(launch_linear(ws.s, W[PF_B_PROJ_W], W[PF_B_PROJ_B], nullptr, nullptr, ws.proj, M, 128, NPROJ, 0, st));
+    // IPA (ga.py:98-104); with chains the projection was produced by the previous chain
+    if (!chains)
+      PF_TRY(launch_linear(ws.s, W[PF_B_PROJ_W], W[PF_B_PROJ_B], nullptr, nullptr, ws.proj, M, 128, NPROJ, 0, st));
     PF_TRY(launch_ipa_points(ws.proj, rot, trans, ws.pts, M, st));
     IpaArgs ia{ws.proj, ws.pts, z, W[PF_B_LINB_W], W[PF_B_LINB_B], W[PF_B_DOWNZ_W], W[PF_B_DOWNZ_B], W[PF_B_HEAD_W],
                rot, trans, res_mask, ws.feats, B, L};
     PF_TRY(launch_ipa_attention(ia, ws.ipa_ws, ws.ipa_ws_bytes, st));
     PF_TRY(launch_linear(ws.feats, W[PF_B_OUT_W], W[PF_B_OUT_B], nullptr, res_mask, ws.ta, M, NFEAT, 128, 0, st));
     PF_TRY(launch_add_layernorm(ws.s, ws.ta, W[PF_B_IPA_LN_G], W[PF_B_IPA_LN_B], nullptr, ws.s, M, 128, st));
-    // sequence transformer, 2 post-norm layers (ga.py:105-106)
-    const float* x = ws.s;
-    float* outs[2] = {ws.ya, ws.yb};
-    for (int l = 0; l < 2; ++l) {
-      const int o = l == 0 ? PF_B_T0_IN_W : PF_B_T1_IN_W;
-      PF_TRY(launch_linear(x, W[o + 0], W[o + 1], nullptr, nullptr, ws.qkv, M, 128, 384, 0, st));
-      PF_TRY(launch_seq_attention(ws.qkv, res_mask, ws.ctx, B, L, st));
-      PF_TRY(launch_linear(ws.ctx, W[o + 2], W[o + 3], nullptr, nullptr, ws.ta, M, 128, 128, 0, st));
-      PF_TRY(launch_add_layernorm(x, ws.ta, W[o + 8], W[o + 9], nullptr, outs[l], M, 128, st));      // norm1
-      PF_TRY(launch_linear(outs[l], W[o + 4], W[o + 5], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));  // linear1+relu
-      PF_TRY(launch_linear(ws.tb, W[o + 6], W[o + 7], nullptr, nullptr, ws.ta, M, 128, 128, 0, st));     // linear2
-      PF_TRY(launch_add_layernorm(outs[l], ws.ta, W[o + 10], W[o + 11], nullptr, outs[l], M, 128, st)); // norm2
-      x = outs[l];
-    }
-    // s += post_tfmr(y)  (ga.py:107)
-    PF_TRY(launch_linear(x, W[PF_B_POST_W], W[PF_B_POST_B], ws.s, nullptr, ws.s, M, 128, 128, 0, st));
-    // node transition (ipa_pytorch.py:196-206) then mask (ga.py:108-109)
-    PF_TRY(launch_linear(ws.s, W[PF_B_NT1_W], W[PF_B_NT1_B], nullptr, nullptr, ws.ta, M, 128, 128, 1, st));
-    PF_TRY(launch_linear(ws.ta, W[PF_B_NT2_W], W[PF_B_NT2_B], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));
-    PF_TRY(launch_linear(ws.tb, W[PF_B_NT3_W], W[PF_B_NT3_B], nullptr, nullptr, ws.ta, M, 128, 128, 0, st));
-    PF_TRY(launch_add_layernorm(ws.s, ws.ta, W[PF_B_NT_LN_G], W[PF_B_NT_LN_B], res_mask, ws.s, M, 128, st));
-    // backbone update (ga.py:110-113)
-    PF_TRY(launch_linear(ws.s, W[PF_B_BB_W], W[PF_B_BB_B], nullptr, nullptr, ws.upd, M, 128, 6, 0, st));
     const bool last = (b == nb - 1);
+    if (chains) {
+      // sequence transformer (ga.py:105-106), post_tfmr (:107), node transition (:108-109), backbone update (:110) and
+      // the next block's IPA projection: two attention launches and two layer chains
+      const int o0 = PF_B_T0_IN_W, o1 = PF_B_T1_IN_W;
+      PF_TRY(launch_linear(ws.s, W[o0], W[o0 + 1], nullptr, nullptr, ws.qkv, M, 128, 384, 0, st));
+      PF_TRY(launch_seq_attention(ws.qkv, res_mask, ws.ctx, B, L, st));
+      {
+        std::vector<NodeChainStage> c;
+        NodeChainStage q = stage(W[o0 + 2], W[o0 + 3], 128, 0);                       // out_proj, norm1(x + .)
+        q.res = ws.s; q.gamma = W[o0 + 8]; q.beta = W[o0 + 9]; q.save_res = q.next_a = true;
+        c.push_back(q);
+        q = stage(W[o0 + 4], W[o0 + 5], 128, 1); q.next_a = true;                     // linear1 + relu
+        c.push_back(q);
+        q = stage(W[o0 + 6], W[o0 + 7], 128, 0);                                      // linear2, norm2(y + .)
+        q.res_from_chain = true; q.gamma = W[o0 + 10]; q.beta = W[o0 + 11]; q.out = ws.ya; q.next_a = true;
+        c.push_back(q);
+        q = stage(W[o1], W[o1 + 1], 384, 0); q.out = ws.qkv;                          // layer 1 in_proj
+        c.push_back(q);
+        PF_TRY(run_chain(ws.ctx, c));
+      }
+      PF_TRY(launch_seq_attention(ws.qkv, res_mask, ws.ctx, B, L, st));
+      {
+        std::vector<NodeChainStage> c;
+        NodeChainStage q = stage(W[o1 + 2], W[o1 + 3], 128, 0);
+        q.res = ws.ya; q.gamma = W[o1 + 8]; q.beta = W[o1 + 9]; q.save_res = q.next_a = true;
+        c.push_back(q);
+        q = stage(W[o1 + 4], W[o1 + 5], 128, 1); q.next_a = true;
+        c.push_back(q);
+        q = stage(W[o1 + 6], W[o1 + 7], 128, 0);
+        q.res_from_chain = true; q.gamma = W[o1 + 10]; q.beta = W[o1 + 11]; q.next_a = true;
+        c.push_back(q);
+        q = stage(W[PF_B_POST_W], W[PF_B_POST_B], 128, 0);                            // s += post_tfmr(y)
+        q.res = ws.s; q.save_res = q.next_a = true;
+        c.push_back(q);
+        q = stage(W[PF_B_NT1_W], W[PF_B_NT1_B], 128, 1); q.next_a = true;
+        c.push_back(q);
+        q = stage(W[PF_B_NT2_W], W[PF_B_NT2_B], 128, 1); q.next_a = true;
+        c.push_back(q);
+        q = stage(W[PF_B_NT3_W], W[PF_B_NT3_B], 128, 0);                              // LN(s + .) * mask -> s
+        q.res_from_chain = true; q.gamma = W[PF_B_NT_LN_G]; q.beta = W[PF_B_NT_LN_B]; q.rowmask = res_mask;
+        q.out = ws.s; q.next_a = true;
+        c.push_back(q);
+        q = stage(W[PF_B_BB_W], W[PF_B_BB_B], 6, 0); q.out = ws.upd;
+        c.push_back(q);
+        if (!last) {
+          PF_REQUIRE(w->blk[b + 1][PF_B_PROJ_W], PF_ERR_NULL_POINTER);
+          c.push_back(proj_stage(b + 1));
+        }
+        PF_TRY(run_chain(ws.ctx, c));
+      }
+    } else {
+      // sequence transformer, 2 post-norm layers (ga.py:105-106)
+      const float* x = ws.s;
+      float* outs[2] = {ws.ya, ws.yb};
+      for (int l = 0; l < 2; ++l) {
+        const int o = l == 0 ? PF_B_T0_IN_W : PF_B_T1_IN_W;
+        PF_TRY(launch_linear(x, W[o + 0], W[o + 1], nullptr, nullptr, ws.qkv, M, 128, 384, 0, st));
+        PF_TRY(launch_seq_attention(ws.qkv, res_mask, ws.ctx, B, L, st));
+        PF_TRY(launch_linear(ws.ctx, W[o + 2], W[o + 3], nullptr, nullptr, ws.ta, M, 128, 128, 0, st));
+        PF_TRY(launch_add_layernorm(x, ws.ta, W[o + 8], W[o + 9], nullptr, outs[l], M, 128, st));      // norm1
+        PF_TRY(launch_linear(outs[l], W[o + 4], W[o + 5], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));  // linear1+relu
+        PF_TRY(launch_linear(ws.tb, W[o + 6], W[o + 7], nullptr, nullptr, ws.ta, M, 128, 128, 0, st));     // linear2
+        PF_TRY(launch_add_layernorm(outs[l], ws.ta, W[o + 10], W[o + 11], nullptr, outs[l], M, 128, st)); // norm2
+        x = outs[l];
+      }
+      // s += post_tfmr(y)  (ga.py:107)
+      PF_TRY(launch_linear(x, W[PF_B_POST_W], W[PF_B_POST_B], ws.s, nullptr, ws.s, M, 128, 128, 0, st));
+      // node transition (ipa_pytorch.py:196-206) then mask (ga.py:108-109)
+      PF_TRY(launch_linear(ws.s, W[PF_B_NT1_W], W[PF_B_NT1_B], nullptr, nullptr, ws.ta, M, 128, 128, 1, st));
+      PF_TRY(launch_linear(ws.ta, W[PF_B_NT2_W], W[PF_B_NT2_B], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));
+      PF_TRY(launch_linear(ws.tb, W[PF_B_NT3_W], W[PF_B_NT3_B], nullptr, nullptr, ws.ta, M, 128, 128, 0, st));
+      PF_TRY(launch_add_layernorm(ws.s, ws.ta, W[PF_B_NT_LN_G], W[PF_B_NT_LN_B], res_mask, ws.s, M, 128, st));
+      // backbone update (ga.py:110-113)
+      PF_TRY(launch_linear(ws.s, W[PF_B_BB_W], W[PF_B_BB_B], nullptr, nullptr, ws.upd, M, 128, 6, 0, st));
+    }
     float* rot_o = last ? pred_rot : ws.rot;
     float* trans_o = last ? pred_trans : ws.trans;
     PF_TRY(launch_rigid_update(quat, quat ? nullptr : rot, trans, ws.upd, res_mask, ws.quat, rot_o, trans_o, M, st));

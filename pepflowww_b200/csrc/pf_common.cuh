@@ -32,6 +32,7 @@ void* debug_buffer(size_t bytes);
 int opt_edge_impl();
 int opt_gemm_impl();
 int opt_ipa_impl();
+int opt_chain_impl();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -103,6 +104,22 @@ int launch_gemm_umma_pack(const float* w, int ldw, int N, void* wpack, cudaStrea
 int launch_linear_umma(const float* x, const float* w, int ldw, const float* bias, const float* rowmask, float* y,
                        int M, int N, int act, const void* wpack, bool prepacked, cudaStream_t st);
 void gemm_umma_init();
+// One layer of a fused node-level chain (launch_node_chain, pf_gemm_umma.cu): y = act(A W^T + b) [+ res] -> [LayerNorm]
+// -> [* rowmask]; A is the previous layer's y when that layer has next_a, else unchanged.
+struct NodeChainStage {
+  const void* wpack;            // tcgen05 weight image of W [N, 128] (launch_gemm_umma_pack / pf_ga_prepack)
+  const float* bias;            // [N] or null
+  const float* res;             // residual rows in HBM [M, 128], or null
+  const float* gamma; const float* beta;   // LayerNorm, or null
+  const float* rowmask;         // [M] or null
+  float* out;                   // [M, N] stored result, or null
+  int N;                        // layer width; > 128 streams tiles out and must not feed a next layer
+  int act;                      // 1 = ReLU
+  bool res_from_chain;          // add the row saved by an earlier layer (save_res)
+  bool save_res;                // keep this layer's y as the residual row for a later layer
+  bool next_a;                  // y becomes the A operand of the following layers
+};
+int launch_node_chain(const float* x, int M, const NodeChainStage* stages, int n, cudaStream_t st);
 size_t linear_workspace_bytes(int N);
 int launch_linear_ws(const float* x, const float* w, int ldw, const float* bias, const float* residual,
                      const float* rowmask, float* y, int M, int K, int N, int act, void* ws, size_t ws_bytes,

@@ -12,6 +12,8 @@
 // Warps 0-3: row threads (A staging, epilogue); warp 4: MMA issuer + tensor-memory allocation; warp 5: W producer.
 #include <cuda.h>
 
+#include <cstring>
+
 #include "pf_common.cuh"
 #include "pf_split.cuh"
 #include "pf_umma.cuh"
@@ -227,6 +229,264 @@ static int encode_y_map(CUtensorMap* m, float* y, int M, int N) {
   return r == CUDA_SUCCESS ? PF_OK : static_cast<int>(cudaErrorInvalidValue);
 }
 
+
+// =================================================================================================
+// Node-level layer chains ("chain_impl" = 1): a run of K = 128 Linear layers with their bias / ReLU / residual /
+// LayerNorm / row-mask epilogues (models_con/ga.py:105-113 - transformer tail, post_tfmr, node transition,
+// backbone update, the next block's IPA projection) as ONE kernel.  Same machinery as gemm_umma_kernel - one CTA per
+// 128-row block, A operand in tensor memory, packed W tiles through a 2-stage ring, two alternating accumulators -
+// but the epilogue of a layer, instead of going to HBM, converts its fp32 row in place into the fp16 hi | lo A
+// operand of the next layer.  LayerNorm is thread-local (a row thread owns one full 128-channel row); the residual
+// stream lives in 128 further tensor-memory columns (or is read from HBM for the first use).  Layers whose output is
+// needed later are also staged in shared memory and stored by TMA; a layer wider than 128 (in_proj, IPA projection)
+// streams its tiles out like the plain GEMM and must not feed a next layer.
+constexpr int CH_MAXS = 10;
+constexpr uint32_t CH_COL_RES = 384;   // fp32 residual row, 128 columns
+enum { CH_NEXT_A = 1, CH_SAVE_RES = 2, CH_RES_TMEM = 4 };
+
+struct ChainStage {
+  const uint4* wpack;            // packed W tiles (launch_gemm_umma_pack)
+  const float* bias;             // [N] or null
+  const float* res;              // residual rows in HBM [M, 128] or null
+  const float* gamma; const float* beta;   // LayerNorm over the 128 channels, or null
+  const float* rowmask;          // [M] or null
+  float* out;                    // [M, N] or null
+  int N, act, flags, pad;
+};
+struct alignas(64) ChainArgs {
+  CUtensorMap tm[CH_MAXS];       // out of stage s as [M, N] fp32, box [128 rows, 32 cols], 128-byte swizzle
+  ChainStage st[CH_MAXS];
+  const float* x;                // [M, 128] input of the first layer
+  int M, nstages;
+};
+
+__global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_constant__ ChainArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + GU_SM_BAR;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + GU_SM_TMEM);
+  float* sbias = reinterpret_cast<float*>(smem + GU_SM_BIAS);
+  const int m0 = blockIdx.x * 128;
+
+  if ((sbase & 1023u) != 0) __trap();
+  if (warp == 4) tmem_alloc_cta(sbase + GU_SM_TMEM, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(GU_BAR_WFULL + i), 1);
+      mbar_init(bar(GU_BAR_WEMPTY + i), 1);
+      mbar_init(bar(GU_BAR_ACCFULL + i), 1);
+      mbar_init(bar(GU_BAR_ACCEMPTY + i), 4);
+    }
+    mbar_init(bar(GU_BAR_A), 4);
+    fence_mbar_init();
+    for (int s = 0; s < a.nstages; ++s)
+      if (a.st[s].out) tma_prefetch_desc(&a.tm[s]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp < 4) {
+    // ================================ row threads ================================================
+    const int rl = warp * 32 + lane, m = m0 + rl;
+    const bool live = m < a.M;
+    const uint32_t tlane = static_cast<uint32_t>(warp * 32) << 16;
+    float v[128];
+    // fp32 row -> fp16 hi | lo A operand in tensor memory, then hand it to the MMA warp
+    auto publish_a = [&]() {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) split_pair(v[32 * c + 2 * q], v[32 * c + 2 * q + 1], hi[q], lo[q]);
+        tmem_st16(tmem + tlane + GU_COL_A + 32 * c, hi);
+        tmem_st16(tmem + tlane + GU_COL_A + 32 * c + 16, lo);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(GU_BAR_A));
+    };
+    {
+      const float4* xp = reinterpret_cast<const float4*>(a.x + (size_t)(live ? m : 0) * 128);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float4 t4 = live ? __ldg(xp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+      }
+      publish_a();
+    }
+    unsigned char* orow = smem + GU_SM_OUT + rl * 128;        // + box * 16384; 16-byte chunk q at q ^ (rl & 7)
+    const int r8 = rl & 7;
+    int it = 0;                                               // tile counter over all stages
+    bool stores_pending = false;
+    for (int s = 0; s < a.nstages; ++s) {
+      const ChainStage& st = a.st[s];
+      const int ntiles = (st.N + 127) / 128;
+      const float rm = (st.rowmask && live) ? st.rowmask[m] : 1.f;
+      for (int nt = 0; nt < ntiles; ++nt, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1u;
+        {
+          const int n = nt * 128 + rl;
+          sbias[buf * 128 + rl] = (st.bias && n < st.N) ? st.bias[n] : 0.f;
+        }
+        mbar_wait(bar(GU_BAR_ACCFULL + buf), ph);
+        tc_fence_after();
+        // earlier TMA stores must have read the staging buffer before it is overwritten
+        if (stores_pending && tid == 0) bulk_wait_read0();
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        const float* bs = sbias + buf * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem + tlane + GU_COL_ACC + 128 * buf + 32 * c, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            float x = __uint_as_float(r[q]) + bs[32 * c + q];
+            if (st.act == 1) x = fmaxf(x, 0.f);
+            v[32 * c + q] = x;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(GU_BAR_ACCEMPTY + buf));   // accumulator may be overwritten
+        if (st.res) {
+          const float4* rp = reinterpret_cast<const float4*>(st.res + (size_t)(live ? m : 0) * 128);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const float4 t4 = live ? __ldg(rp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * q] += t4.x; v[4 * q + 1] += t4.y; v[4 * q + 2] += t4.z; v[4 * q + 3] += t4.w;
+          }
+        }
+        if (st.flags & CH_RES_TMEM) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem + tlane + CH_COL_RES + 32 * c, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[32 * c + q] += __uint_as_float(r[q]);
+          }
+        }
+        if (st.gamma) {
+          float sum = 0.f;
+#pragma unroll
+          for (int q = 0; q < 128; ++q) sum += v[q];
+          const float mu = sum * (1.0f / 128.0f);
+          float sq = 0.f;
+#pragma unroll
+          for (int q = 0; q < 128; ++q) { const float d = v[q] - mu; sq = fmaf(d, d, sq); }
+          const float rstd = 1.0f / sqrtf(sq * (1.0f / 128.0f) + 1e-5f);
+#pragma unroll
+          for (int q = 0; q < 128; ++q) v[q] = (v[q] - mu) * rstd * __ldg(st.gamma + q) + __ldg(st.beta + q);
+        }
+        if (st.rowmask) {
+#pragma unroll
+          for (int q = 0; q < 128; ++q) v[q] *= rm;
+        }
+        const bool tma_out = st.out && (st.N & 3) == 0;
+        if (tma_out) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            unsigned char* box = orow + c * 16384;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(box + ((q ^ r8) << 4)) =
+                  make_float4(v[32 * c + 4 * q], v[32 * c + 4 * q + 1], v[32 * c + 4 * q + 2], v[32 * c + 4 * q + 3]);
+          }
+        } else if (st.out && live) {                          // narrow output (backbone update: N = 6)
+#pragma unroll
+          for (int n = 0; n < 8; ++n)
+            if (n < st.N) st.out[(size_t)m * st.N + n] = v[n];
+        }
+        if (st.flags & CH_SAVE_RES) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t r[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) r[q] = __float_as_uint(v[16 * c + q]);
+            tmem_st16(tmem + tlane + CH_COL_RES + 16 * c, r);
+          }
+          tc_wait_st();
+        }
+        if (st.flags & CH_NEXT_A) publish_a();
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (tma_out && tid == 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (nt * 128 + 32 * c < st.N) tma_store_2d(&a.tm[s], nt * 128 + 32 * c, m0, sbase + GU_SM_OUT + c * 16384);
+          bulk_commit();
+        }
+        stores_pending = stores_pending || tma_out;
+      }
+    }
+    if (tid == 0) bulk_wait0();
+  } else if (warp == 4) {
+    // ================================ MMA issuer ==================================================
+    const uint32_t idesc = idesc_f16(128, 128);
+    int it = 0;
+    uint32_t a_ph = 0;
+    bool a_new = true;
+    for (int s = 0; s < a.nstages; ++s) {
+      const int ntiles = (a.st[s].N + 127) / 128;
+      if (a_new) {                                            // the A operand was (re)written by the row threads
+        mbar_wait(bar(GU_BAR_A), a_ph);
+        a_ph ^= 1u;
+        tc_fence_after();
+      }
+      a_new = (a.st[s].flags & CH_NEXT_A) != 0;
+      for (int nt = 0; nt < ntiles; ++nt, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1u;
+        mbar_wait(bar(GU_BAR_WFULL + buf), ph);
+        if (it >= 2) mbar_wait(bar(GU_BAR_ACCEMPTY + buf), ((it >> 1) - 1) & 1u);
+        tc_fence_after();
+        const uint32_t wt = sbase + GU_SM_W + buf * GU_TILE_BYTES;
+        const uint32_t d = tmem + GU_COL_ACC + 128 * buf;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t dh = smem_desc(wt + ks * 4096, 2048, 128);
+          const uint64_t dl = smem_desc(wt + 32768 + ks * 4096, 2048, 128);
+          const uint32_t a_hi = tmem + GU_COL_A + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
+          if (elect_one()) {
+            mma_cta_ts(d, a_lo, dh, idesc, ks == 0 ? 0u : 1u);
+            mma_cta_ts(d, a_hi, dl, idesc, 1u);
+            mma_cta_ts(d, a_hi, dh, idesc, 1u);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          commit_cta(bar(GU_BAR_WEMPTY + buf));
+          commit_cta(bar(GU_BAR_ACCFULL + buf));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (lane == 0) {
+    // ================================ W producer ==================================================
+    int it = 0;
+    for (int s = 0; s < a.nstages; ++s) {
+      const int ntiles = (a.st[s].N + 127) / 128;
+      for (int nt = 0; nt < ntiles; ++nt, ++it) {
+        const int buf = it & 1;
+        if (it >= 2) mbar_wait(bar(GU_BAR_WEMPTY + buf), ((it >> 1) - 1) & 1u);
+        mbar_arrive_expect_tx(bar(GU_BAR_WFULL + buf), GU_TILE_BYTES);
+        bulk_g2s(sbase + GU_SM_W + buf * GU_TILE_BYTES, a.st[s].wpack + (size_t)nt * 4096, GU_TILE_BYTES,
+                 bar(GU_BAR_WFULL + buf));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc_cta(tmem, 512);
+}
+
 size_t gemm_umma_pack_bytes(int N) { return (size_t)((N + 127) / 128) * GU_TILE_BYTES; }
 
 // Preconditions (checked by the caller): K == 128, N % 4 == 0, x / y 16-byte aligned, no residual.
@@ -251,8 +511,37 @@ int launch_linear_umma(const float* x, const float* w, int ldw, const float* bia
   return PF_OK;
 }
 
+// Host side of the chain: validates the layer list, encodes one tensor map per stored output, launches.
+int launch_node_chain(const float* x, int M, const NodeChainStage* stages, int n, cudaStream_t st) {
+  PF_REQUIRE(x && stages && n >= 1 && n <= CH_MAXS, PF_ERR_BAD_CONFIG);
+  if (M == 0) return PF_OK;
+  ChainArgs a;
+  std::memset(&a, 0, sizeof(a));
+  for (int s = 0; s < n; ++s) {
+    const NodeChainStage& h = stages[s];
+    PF_REQUIRE(h.wpack && h.N >= 1, PF_ERR_NULL_POINTER);
+    const bool rowwise = h.res || h.gamma || h.res_from_chain || h.save_res || h.next_a;
+    PF_REQUIRE(!rowwise || h.N == 128, PF_ERR_BAD_SHAPE);             // row-wise epilogues need the whole row in one tile
+    PF_REQUIRE((h.gamma == nullptr) == (h.beta == nullptr), PF_ERR_NULL_POINTER);
+    PF_REQUIRE(!h.out || (h.N & 3) == 0 || h.N <= 8, PF_ERR_BAD_SHAPE);
+    ChainStage& d = a.st[s];
+    d.wpack = static_cast<const uint4*>(h.wpack); d.bias = h.bias; d.res = h.res; d.gamma = h.gamma; d.beta = h.beta;
+    d.rowmask = h.rowmask; d.out = h.out; d.N = h.N; d.act = h.act;
+    d.flags = (h.next_a ? CH_NEXT_A : 0) | (h.save_res ? CH_SAVE_RES : 0) | (h.res_from_chain ? CH_RES_TMEM : 0);
+    if (h.out && (h.N & 3) == 0) {
+      PF_REQUIRE(aligned16(h.out), PF_ERR_MISALIGNED);
+      PF_TRY(encode_y_map(&a.tm[s], h.out, M, h.N));
+    }
+  }
+  a.x = x; a.M = M; a.nstages = n;
+  node_chain_kernel<<<(M + 127) / 128, GU_THREADS, GU_SMEM, st>>>(a);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
 void gemm_umma_init() {
   cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GU_SMEM);
+  cudaFuncSetAttribute(node_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GU_SMEM);
 }
 
 }  // namespace pf

@@ -33,19 +33,22 @@ def model(dev, state_dict):
     return m.to(dev)
 
 
-@pytest.fixture(params=[(0, 0, 0), (2, 2, 4), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4)],
-                ids=["fp32", "tc", "edge_mma_sync", "edge_tcgen05", "gemm_mma_sync", "gemm_tcgen05", "ipa_tc_v1",
-                     "ipa_tc_v2", "ipa_tc_v3", "ipa_tc_v4"])
+@pytest.fixture(params=[(0, 0, 0, 1), (2, 2, 4, 1), (2, 2, 4, 0), (1, 0, 0, 1), (2, 0, 0, 1), (0, 1, 0, 1), (0, 2, 0, 1),
+                        (0, 2, 0, 0), (0, 0, 1, 1), (0, 0, 2, 1), (0, 0, 3, 1), (0, 0, 4, 1)],
+                ids=["fp32", "tc", "tc_unfused_layers", "edge_mma_sync", "edge_tcgen05", "gemm_mma_sync", "gemm_tcgen05_chains",
+                     "gemm_tcgen05", "ipa_tc_v1", "ipa_tc_v2", "ipa_tc_v3", "ipa_tc_v4"])
 def impl(request):
     from pepflowww_b200 import _lib
-    edge, gemm, ipa = request.param
+    edge, gemm, ipa, chain = request.param
     _lib.set_option("edge_impl", edge)
     _lib.set_option("gemm_impl", gemm)
     _lib.set_option("ipa_impl", ipa)
+    _lib.set_option("chain_impl", chain)
     yield request.param
     _lib.set_option("edge_impl", 2)
     _lib.set_option("gemm_impl", 2)
     _lib.set_option("ipa_impl", 4)
+    _lib.set_option("chain_impl", 1)
 
 
 def cu(g, dev, keys):
