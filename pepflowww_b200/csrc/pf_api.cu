@@ -102,13 +102,17 @@ static GaWorkspace carve(void* base, int B, int L) {
 // ---- prepacked weight images (pf_ga_prepack) -----------------------------------------------------
 // Every K = 128 Linear that takes the tcgen05 GEMM and every block's edge-transition MLP; the order below
 // defines the offsets inside the buffer, so pf_ga_prepack and pf_ga_encoder_forward agree by construction.
-struct PackItem { const float* w; int N; size_t off; bool edge; const float* w2; const float* wf; };
+// kind 0: tcgen05 tiles of a K = 128 Linear; 1: edge-transition MLP image; 2: composed per-residue edge terms
+// (fp32 Wc [512,128] | bc [512] | tiles of the P, Q, U, V row groups)
+struct PackItem { const float* w; int N; size_t off; bool edge; const float* w2; const float* wf; int kind; int blk; };
+constexpr size_t TERMS_WC = 0, TERMS_BC = 512 * 128 * 4, TERMS_TILES = TERMS_BC + 2048;
+constexpr int TERMS_ROW[4] = {0, 192, 384, 448}, TERMS_N[4] = {192, 192, 64, 64}, TERMS_TILE0[4] = {0, 2, 4, 5};
 
 static size_t enumerate_packables(const pf_ga_weights* w, std::vector<PackItem>* items) {
   size_t off = 0;
   auto lin = [&](const float* p, int N) {
     if (!p) return;
-    if (items) items->push_back(PackItem{p, N, off, false, nullptr, nullptr});
+    if (items) items->push_back(PackItem{p, N, off, false, nullptr, nullptr, 0, -1});
     off += al(gemm_umma_pack_bytes(N));
   };
   lin(w->g[PF_G_MIX2_W], 128);
@@ -123,8 +127,12 @@ static size_t enumerate_packables(const pf_ga_weights* w, std::vector<PackItem>*
     lin(W[PF_B_NT1_W], 128); lin(W[PF_B_NT2_W], 128); lin(W[PF_B_NT3_W], 128);
     lin(W[PF_B_POST_W], 128); lin(W[PF_B_BB_W], 6);
     if (W[PF_B_ET_W1] && W[PF_B_ET_W2] && W[PF_B_ET_WF]) {
-      if (items) items->push_back(PackItem{W[PF_B_ET_W1], 0, off, true, W[PF_B_ET_W2], W[PF_B_ET_WF]});
+      if (items) items->push_back(PackItem{W[PF_B_ET_W1], 0, off, true, W[PF_B_ET_W2], W[PF_B_ET_WF], 1, b});
       off += al(edge_umma_weight_image_bytes());
+      if (W[PF_B_ET_INIT_W] && W[PF_B_ET_INIT_B] && W[PF_B_ET_B1] && W[PF_B_ET_BF]) {
+        if (items) items->push_back(PackItem{W[PF_B_ET_INIT_W], 0, off, false, nullptr, nullptr, 2, b});
+        off += al(TERMS_TILES + 6 * gemm_umma_pack_bytes(128));
+      }
     }
   }
   return off;
@@ -152,8 +160,20 @@ int pf_ga_prepack(const pf_ga_weights* w, void* buffer, size_t buffer_bytes, voi
   unsigned char* base = static_cast<unsigned char*>(buffer);
   cudaStream_t st = as_stream(stream);
   for (const PackItem& it : items) {
-    if (it.edge) PF_TRY(launch_edge_umma_pack_weights(it.w, it.w2, it.wf, base + it.off, st));
-    else PF_TRY(launch_gemm_umma_pack(it.w, 128, it.N, base + it.off, st));
+    if (it.kind == 1) {
+      PF_TRY(launch_edge_umma_pack_weights(it.w, it.w2, it.wf, base + it.off, st));
+    } else if (it.kind == 2) {
+      const float* const* W = w->blk[it.blk];
+      float* wc = reinterpret_cast<float*>(base + it.off + TERMS_WC);
+      float* bc = reinterpret_cast<float*>(base + it.off + TERMS_BC);
+      PF_TRY(launch_edge_compose_terms(W[PF_B_ET_INIT_W], W[PF_B_ET_INIT_B], W[PF_B_ET_W1], W[PF_B_ET_B1], W[PF_B_ET_WF],
+                                       W[PF_B_ET_BF], wc, bc, st));
+      for (int q = 0; q < 4; ++q)
+        PF_TRY(launch_gemm_umma_pack(wc + (size_t)TERMS_ROW[q] * 128, 128, TERMS_N[q],
+                                     base + it.off + TERMS_TILES + TERMS_TILE0[q] * gemm_umma_pack_bytes(128), st));
+    } else {
+      PF_TRY(launch_gemm_umma_pack(it.w, 128, it.N, base + it.off, st));
+    }
   }
   return PF_OK;
 }
@@ -286,7 +306,12 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
   if (w->prepacked && w->prepacked_bytes >= enumerate_packables(w, nullptr)) enumerate_packables(w, &packed);
   auto find_packed = [&](const float* wt, bool edge) -> const void* {
     for (const PackItem& it : packed)
-      if (it.w == wt && it.edge == edge) return static_cast<const unsigned char*>(w->prepacked) + it.off;
+      if (it.w == wt && it.edge == edge && it.kind != 2) return static_cast<const unsigned char*>(w->prepacked) + it.off;
+    return nullptr;
+  };
+  auto find_terms = [&](int blk) -> const unsigned char* {
+    for (const PackItem& it : packed)
+      if (it.kind == 2 && it.blk == blk) return static_cast<const unsigned char*>(w->prepacked) + it.off;
     return nullptr;
   };
   auto launch_linear = [&](const float* x, const float* wt, const float* bias, const float* residual,
@@ -347,6 +372,7 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
     PF_TRY(launch_linear(ws.feats, W[PF_B_OUT_W], W[PF_B_OUT_B], nullptr, res_mask, ws.ta, M, NFEAT, 128, 0, st));
     PF_TRY(launch_add_layernorm(ws.s, ws.ta, W[PF_B_IPA_LN_G], W[PF_B_IPA_LN_B], nullptr, ws.s, M, 128, st));
     const bool last = (b == nb - 1);
+    bool terms_ready = false;
     if (chains) {
       // sequence transformer (ga.py:105-106), post_tfmr (:107), node transition (:108-109), backbone update (:110) and
       // the next block's IPA projection: two attention launches and two layer chains
@@ -392,6 +418,20 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
         q = stage(W[PF_B_BB_W], W[PF_B_BB_B], 6, 0); q.out = ws.upd;
         c.push_back(q);
         if (!last) {
+          // the per-residue terms of this block's edge transition, straight from the new s (composed weights)
+          const unsigned char* tw = opt_edge_impl() != 0 ? find_terms(b) : nullptr;
+          if (tw) {
+            float* dst[4];
+            edge_term_buffers(ws.edge_ws, B, L, &dst[0], &dst[1], &dst[2], &dst[3]);
+            const float* bc = reinterpret_cast<const float*>(tw + TERMS_BC);
+            for (int t4 = 0; t4 < 4; ++t4) {
+              NodeChainStage e{};
+              e.wpack = tw + TERMS_TILES + TERMS_TILE0[t4] * gemm_umma_pack_bytes(128);
+              e.bias = bc + TERMS_ROW[t4]; e.N = TERMS_N[t4]; e.out = dst[t4];
+              c.push_back(e);
+            }
+            terms_ready = true;
+          }
           PF_REQUIRE(w->blk[b + 1][PF_B_PROJ_W], PF_ERR_NULL_POINTER);
           c.push_back(proj_stage(b + 1));
         }
@@ -431,7 +471,7 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
       PF_TRY(launch_edge_transition(ws.s, z, W[PF_B_ET_INIT_W], W[PF_B_ET_INIT_B], W[PF_B_ET_W1], W[PF_B_ET_B1],
                                     W[PF_B_ET_W2], W[PF_B_ET_B2], W[PF_B_ET_WF], W[PF_B_ET_BF], W[PF_B_ET_LN_G],
                                     W[PF_B_ET_LN_B], res_mask, ws.zbuf, ws.edge_ws, ws.edge_ws_bytes, B, L, st,
-                                    find_packed(W[PF_B_ET_W1], true)));
+                                    find_packed(W[PF_B_ET_W1], true), terms_ready));
       z = ws.zbuf;
     }
   }

@@ -151,7 +151,10 @@ int launch_edge_transition(const float* s, const float* z_in, const float* w_ini
                            const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
                            const float* bf, const float* ln_g, const float* ln_b, const float* mask, float* z_out,
                            void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st,
-                           const void* prepacked_weights = nullptr);
+                           const void* prepacked_weights = nullptr, bool terms_ready = false);
+void edge_term_buffers(void* workspace, int B, int L, float** P, float** Q, float** U, float** V);
+int launch_edge_compose_terms(const float* w_init, const float* b_init, const float* w1, const float* b1,
+                              const float* wf, const float* bf, float* wc, float* bc, cudaStream_t st);
 // 128-byte CUtensorMap over a pair tensor z [B, L, L, 64] fp32 viewed as (c: 64, j: L, bi: B*L), boxes of
 // [32 c, 8 j, 1 bi] = 1 KB with the 128-byte swizzle (shared by the edge-transition and IPA kernels)
 int encode_z_map(void* tensor_map, const float* z, int B, int L);

@@ -431,17 +431,63 @@ size_t edge_workspace_bytes(int B, int L) {
          align256(E1_STREAM_BYTES) + align256(edge_umma_pack_bytes(B, L));
 }
 
+// The per-residue terms of the hoisted first / last layer inside the edge-transition workspace
+void edge_term_buffers(void* workspace, int B, int L, float** P, float** Q, float** U, float** V) {
+  const size_t M = (size_t)B * L;
+  unsigned char* ws = static_cast<unsigned char*>(workspace) + align256(M * 64 * 4);
+  *P = reinterpret_cast<float*>(ws); ws += align256(M * 192 * 4);
+  *Q = reinterpret_cast<float*>(ws); ws += align256(M * 192 * 4);
+  *U = reinterpret_cast<float*>(ws); ws += align256(M * 64 * 4);
+  *V = reinterpret_cast<float*>(ws);
+}
+
+// P = W1[:, 64:128] e + b1, Q = W1[:, 128:192] e, U = Wf[:, 64:128] e + bf, V = Wf[:, 128:192] e with
+// e = W_init s + b_init (ipa_pytorch.py:233-241) are all linear in the node row s: compose them once into
+// Wc [512, 128] (rows P 0-191 | Q 192-383 | U 384-447 | V 448-511) and bc [512], so the node-layer chain can emit
+// the four terms straight from s as extra layers.
+__global__ void edge_compose_terms_kernel(const float* __restrict__ w_init, const float* __restrict__ b_init,
+                                          const float* __restrict__ w1, const float* __restrict__ b1,
+                                          const float* __restrict__ wf, const float* __restrict__ bf,
+                                          float* __restrict__ wc, float* __restrict__ bc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // (row n of Wc, column k) or, past 512 * 128, a bias entry
+  const bool is_bias = idx >= 512 * 128;
+  const int n = is_bias ? idx - 512 * 128 : idx >> 7, k = idx & 127;
+  if (n >= 512) return;
+  const float* row;                                           // 64 coefficients over e
+  float add = 0.f;
+  if (n < 192) { row = w1 + (size_t)n * 192 + 64; add = b1[n]; }
+  else if (n < 384) { row = w1 + (size_t)(n - 192) * 192 + 128; }
+  else if (n < 448) { row = wf + (size_t)(n - 384) * 192 + 64; add = bf[n - 384]; }
+  else { row = wf + (size_t)(n - 448) * 192 + 128; }
+  float acc = 0.f;
+  if (is_bias) {
+    for (int c = 0; c < 64; ++c) acc = fmaf(row[c], b_init[c], acc);
+    bc[n] = acc + add;
+  } else {
+    for (int c = 0; c < 64; ++c) acc = fmaf(row[c], w_init[c * 128 + k], acc);
+    wc[(size_t)n * 128 + k] = acc;
+  }
+}
+
+int launch_edge_compose_terms(const float* w_init, const float* b_init, const float* w1, const float* b1,
+                              const float* wf, const float* bf, float* wc, float* bc, cudaStream_t st) {
+  edge_compose_terms_kernel<<<(512 * 128 + 512 + 255) / 256, 256, 0, st>>>(w_init, b_init, w1, b1, wf, bf, wc, bc);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
 int launch_edge_transition(const float* s, const float* z_in, const float* w_init, const float* b_init,
                            const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
                            const float* bf, const float* ln_g, const float* ln_b, const float* mask, float* z_out,
                            void* workspace, size_t workspace_bytes, int B, int L, cudaStream_t st,
-                           const void* prepacked_weights) {
+                           const void* prepacked_weights, bool terms_ready) {
   if (B == 0 || L == 0) return PF_OK;
   PF_REQUIRE(workspace_bytes >= edge_workspace_bytes(B, L), PF_ERR_WORKSPACE_TOO_SMALL);
+  PF_REQUIRE(!terms_ready || opt_edge_impl() != 0, PF_ERR_BAD_CONFIG);
   const int M = B * L;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   float* e = reinterpret_cast<float*>(ws); ws += align256((size_t)M * 64 * 4);
-  PF_TRY(launch_linear(s, w_init, b_init, nullptr, nullptr, e, M, 128, 64, 0, st));
+  if (!terms_ready) PF_TRY(launch_linear(s, w_init, b_init, nullptr, nullptr, e, M, 128, 64, 0, st));
   if (opt_edge_impl() == 0) {
     EdgeArgs a{e, z_in, w1, b1, w2, b2, wf, bf, ln_g, ln_b, mask, z_out, B, L};
     dim3 grid((L * L + E0_ROWS - 1) / E0_ROWS, B);
@@ -458,10 +504,12 @@ int launch_edge_transition(const float* s, const float* z_in, const float* w_ini
   uint4* w2pack = reinterpret_cast<uint4*>(ws); ws += align256(E1_W2_BYTES);
   uint4* stream = reinterpret_cast<uint4*>(ws); ws += align256(E1_STREAM_BYTES);
   void* upack = ws;
-  PF_TRY(launch_linear_ld(e, w1 + 64, 192, b1, P, M, 64, 192, st));
-  PF_TRY(launch_linear_ld(e, w1 + 128, 192, nullptr, Q, M, 64, 192, st));
-  PF_TRY(launch_linear_ld(e, wf + 64, 192, bf, U, M, 64, 64, st));
-  PF_TRY(launch_linear_ld(e, wf + 128, 192, nullptr, V, M, 64, 64, st));
+  if (!terms_ready) {
+    PF_TRY(launch_linear_ld(e, w1 + 64, 192, b1, P, M, 64, 192, st));
+    PF_TRY(launch_linear_ld(e, w1 + 128, 192, nullptr, Q, M, 64, 192, st));
+    PF_TRY(launch_linear_ld(e, wf + 64, 192, bf, U, M, 64, 64, st));
+    PF_TRY(launch_linear_ld(e, wf + 128, 192, nullptr, V, M, 64, 64, st));
+  }
   if (opt_edge_impl() == 2)
     return launch_edge_umma(z_in, P, Q, U, V, w1, w2, wf, b2, ln_g, ln_b, mask, z_out, upack, B, L, st,
                             prepacked_weights);

@@ -240,7 +240,7 @@ static int encode_y_map(CUtensorMap* m, float* y, int M, int N) {
 // stream lives in 128 further tensor-memory columns (or is read from HBM for the first use).  Layers whose output is
 // needed later are also staged in shared memory and stored by TMA; a layer wider than 128 (in_proj, IPA projection)
 // streams its tiles out like the plain GEMM and must not feed a next layer.
-constexpr int CH_MAXS = 10;
+constexpr int CH_MAXS = 14;
 constexpr uint32_t CH_COL_RES = 384;   // fp32 residual row, 128 columns
 enum { CH_NEXT_A = 1, CH_SAVE_RES = 2, CH_RES_TMEM = 4 };
 

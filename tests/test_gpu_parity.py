@@ -505,4 +505,4 @@ def test_launch_counter(dev, model):
     _lib.reset_launch_count()
     with torch.no_grad():
         model.ga_encoder(*cu(g, dev, GA_KEYS))
-    assert _lib.launch_count() > 100
+    assert _lib.launch_count() > 50      # ~85 with the fused layer chains (was > 200 with one launch per layer)
