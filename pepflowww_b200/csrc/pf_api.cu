@@ -126,6 +126,10 @@ static size_t enumerate_packables(const pf_ga_weights* w, std::vector<PackItem>*
     }
     lin(W[PF_B_NT1_W], 128); lin(W[PF_B_NT2_W], 128); lin(W[PF_B_NT3_W], 128);
     lin(W[PF_B_POST_W], 128); lin(W[PF_B_BB_W], 6);
+    if (W[PF_B_OUT_W]) {                               // IPA linear_out [128, 1536]: one tile per 128-column chunk
+      if (items) items->push_back(PackItem{W[PF_B_OUT_W], 128, off, false, nullptr, nullptr, 3, b});
+      off += al((NFEAT / 128) * gemm_umma_pack_bytes(128));
+    }
     if (W[PF_B_ET_W1] && W[PF_B_ET_W2] && W[PF_B_ET_WF]) {
       if (items) items->push_back(PackItem{W[PF_B_ET_W1], 0, off, true, W[PF_B_ET_W2], W[PF_B_ET_WF], 1, b});
       off += al(edge_umma_weight_image_bytes());
@@ -171,6 +175,9 @@ int pf_ga_prepack(const pf_ga_weights* w, void* buffer, size_t buffer_bytes, voi
       for (int q = 0; q < 4; ++q)
         PF_TRY(launch_gemm_umma_pack(wc + (size_t)TERMS_ROW[q] * 128, 128, TERMS_N[q],
                                      base + it.off + TERMS_TILES + TERMS_TILE0[q] * gemm_umma_pack_bytes(128), st));
+    } else if (it.kind == 3) {
+      for (int kc = 0; kc < NFEAT / 128; ++kc)
+        PF_TRY(launch_gemm_umma_pack(it.w + kc * 128, NFEAT, 128, base + it.off + kc * gemm_umma_pack_bytes(128), st));
     } else {
       PF_TRY(launch_gemm_umma_pack(it.w, 128, it.N, base + it.off, st));
     }
@@ -369,15 +376,27 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
     IpaArgs ia{ws.proj, ws.pts, z, W[PF_B_LINB_W], W[PF_B_LINB_B], W[PF_B_DOWNZ_W], W[PF_B_DOWNZ_B], W[PF_B_HEAD_W],
                rot, trans, res_mask, ws.feats, B, L};
     PF_TRY(launch_ipa_attention(ia, ws.ipa_ws, ws.ipa_ws_bytes, st));
-    PF_TRY(launch_linear(ws.feats, W[PF_B_OUT_W], W[PF_B_OUT_B], nullptr, res_mask, ws.ta, M, NFEAT, 128, 0, st));
-    PF_TRY(launch_add_layernorm(ws.s, ws.ta, W[PF_B_IPA_LN_G], W[PF_B_IPA_LN_B], nullptr, ws.s, M, 128, st));
+    if (chains) {
+      // linear_out (K = 1536) * mask, LN(s + .) -> s, and the first transformer layer's in_proj: one chain
+      std::vector<NodeChainStage> c;
+      NodeChainStage q = stage(W[PF_B_OUT_W], W[PF_B_OUT_B], 128, 0);
+      q.rowmask = res_mask; q.mask_first = true; q.res = ws.s; q.gamma = W[PF_B_IPA_LN_G]; q.beta = W[PF_B_IPA_LN_B];
+      q.out = ws.s; q.next_a = true;
+      c.push_back(q);
+      q = stage(W[PF_B_T0_IN_W], W[PF_B_T0_IN_B], 384, 0); q.out = ws.qkv;
+      c.push_back(q);
+      for (const NodeChainStage& t : c) PF_REQUIRE(t.wpack, PF_ERR_BAD_CONFIG);
+      PF_TRY(launch_node_chain(ws.feats, M, c.data(), (int)c.size(), st, NFEAT / 128));
+    } else {
+      PF_TRY(launch_linear(ws.feats, W[PF_B_OUT_W], W[PF_B_OUT_B], nullptr, res_mask, ws.ta, M, NFEAT, 128, 0, st));
+      PF_TRY(launch_add_layernorm(ws.s, ws.ta, W[PF_B_IPA_LN_G], W[PF_B_IPA_LN_B], nullptr, ws.s, M, 128, st));
+    }
     const bool last = (b == nb - 1);
     bool terms_ready = false;
     if (chains) {
       // sequence transformer (ga.py:105-106), post_tfmr (:107), node transition (:108-109), backbone update (:110) and
       // the next block's IPA projection: two attention launches and two layer chains
       const int o0 = PF_B_T0_IN_W, o1 = PF_B_T1_IN_W;
-      PF_TRY(launch_linear(ws.s, W[o0], W[o0 + 1], nullptr, nullptr, ws.qkv, M, 128, 384, 0, st));
       PF_TRY(launch_seq_attention(ws.qkv, res_mask, ws.ctx, B, L, st));
       {
         std::vector<NodeChainStage> c;

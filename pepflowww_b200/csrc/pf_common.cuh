@@ -118,8 +118,10 @@ struct NodeChainStage {
   bool res_from_chain;          // add the row saved by an earlier layer (save_res)
   bool save_res;                // keep this layer's y as the residual row for a later layer
   bool next_a;                  // y becomes the A operand of the following layers
+  bool mask_first;              // apply rowmask before the residual / LayerNorm instead of after
 };
-int launch_node_chain(const float* x, int M, const NodeChainStage* stages, int n, cudaStream_t st);
+// kchunks > 1: x is [M, 128 * kchunks] and the first layer contracts all of it (W image: one tile per 128-column chunk)
+int launch_node_chain(const float* x, int M, const NodeChainStage* stages, int n, cudaStream_t st, int kchunks = 1);
 size_t linear_workspace_bytes(int N);
 int launch_linear_ws(const float* x, const float* w, int ldw, const float* bias, const float* residual,
                      const float* rowmask, float* y, int M, int K, int N, int act, void* ws, size_t ws_bytes,

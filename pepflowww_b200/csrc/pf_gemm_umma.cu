@@ -28,7 +28,8 @@ constexpr int GU_SM_W = 0;                     // 2 stages
 constexpr int GU_SM_OUT = 2 * GU_TILE_BYTES;   // 4 boxes of [128 rows][32 cols] fp32, 128-byte swizzle (64 KB)
 constexpr int GU_SM_BIAS = GU_SM_OUT + 65536;  // 128 floats of the current tile (double buffered)
 constexpr int GU_SM_BAR = GU_SM_BIAS + 2 * 128 * 4;
-enum { GU_BAR_WFULL = 0, GU_BAR_WEMPTY = 2, GU_BAR_ACCFULL = 4, GU_BAR_ACCEMPTY = 6, GU_BAR_A = 8, GU_NBARS = 9 };
+enum { GU_BAR_WFULL = 0, GU_BAR_WEMPTY = 2, GU_BAR_ACCFULL = 4, GU_BAR_ACCEMPTY = 6, GU_BAR_A = 8, GU_BAR_A1 = 9,
+       GU_BAR_AFREE = 10, GU_NBARS = 12 };   // A1 / AFREE[2]: second A buffer of the chain kernel's K loop
 constexpr int GU_SM_TMEM = GU_SM_BAR + GU_NBARS * 8 + 8;
 constexpr int GU_SMEM = GU_SM_TMEM + 16;
 static_assert(GU_SM_OUT % 1024 == 0 && GU_SMEM <= 232448, "shared memory layout");
@@ -242,7 +243,7 @@ static int encode_y_map(CUtensorMap* m, float* y, int M, int N) {
 // streams its tiles out like the plain GEMM and must not feed a next layer.
 constexpr int CH_MAXS = 14;
 constexpr uint32_t CH_COL_RES = 384;   // fp32 residual row, 128 columns
-enum { CH_NEXT_A = 1, CH_SAVE_RES = 2, CH_RES_TMEM = 4 };
+enum { CH_NEXT_A = 1, CH_SAVE_RES = 2, CH_RES_TMEM = 4, CH_MASK_FIRST = 8 };
 
 struct ChainStage {
   const uint4* wpack;            // packed W tiles (launch_gemm_umma_pack)
@@ -256,8 +257,11 @@ struct ChainStage {
 struct alignas(64) ChainArgs {
   CUtensorMap tm[CH_MAXS];       // out of stage s as [M, N] fp32, box [128 rows, 32 cols], 128-byte swizzle
   ChainStage st[CH_MAXS];
-  const float* x;                // [M, 128] input of the first layer
+  const float* x;                // [M, 128 * kchunks] input of the first layer
   int M, nstages;
+  int kchunks;                   // > 1: the first layer contracts K = 128 * kchunks (its W image holds one tile per
+                                 // 128-column chunk); the chunks alternate between two A buffers (the second one
+                                 // borrows the residual columns) and accumulate into one tile
 };
 
 __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_constant__ ChainArgs a) {
@@ -280,6 +284,9 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
       mbar_init(bar(GU_BAR_ACCEMPTY + i), 4);
     }
     mbar_init(bar(GU_BAR_A), 4);
+    mbar_init(bar(GU_BAR_A1), 4);
+    mbar_init(bar(GU_BAR_AFREE), 1);
+    mbar_init(bar(GU_BAR_AFREE + 1), 1);
     fence_mbar_init();
     for (int s = 0; s < a.nstages; ++s)
       if (a.st[s].out) tma_prefetch_desc(&a.tm[s]);
@@ -296,28 +303,34 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
     const uint32_t tlane = static_cast<uint32_t>(warp * 32) << 16;
     float v[128];
     // fp32 row -> fp16 hi | lo A operand in tensor memory, then hand it to the MMA warp
-    auto publish_a = [&]() {
+    auto publish_a = [&](int abuf) {
+      const uint32_t col = abuf ? CH_COL_RES : GU_COL_A;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) split_pair(v[32 * c + 2 * q], v[32 * c + 2 * q + 1], hi[q], lo[q]);
-        tmem_st16(tmem + tlane + GU_COL_A + 32 * c, hi);
-        tmem_st16(tmem + tlane + GU_COL_A + 32 * c + 16, lo);
+        tmem_st16(tmem + tlane + col + 32 * c, hi);
+        tmem_st16(tmem + tlane + col + 32 * c + 16, lo);
       }
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(GU_BAR_A));
+      if (lane == 0) mbar_arrive(bar(abuf ? GU_BAR_A1 : GU_BAR_A));
     };
-    {
-      const float4* xp = reinterpret_cast<const float4*>(a.x + (size_t)(live ? m : 0) * 128);
+    for (int kc = 0; kc < a.kchunks; ++kc) {
+      const int abuf = kc & 1;
+      if (kc >= 2) {                                          // the MMAs of chunk kc - 2 have read this buffer
+        mbar_wait(bar(GU_BAR_AFREE + abuf), ((kc >> 1) - 1) & 1u);
+        tc_fence_after();
+      }
+      const float4* xp = reinterpret_cast<const float4*>(a.x + ((size_t)(live ? m : 0) * a.kchunks + kc) * 128);
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
         const float4 t4 = live ? __ldg(xp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
       }
-      publish_a();
+      publish_a(abuf);
     }
     unsigned char* orow = smem + GU_SM_OUT + rl * 128;        // + box * 16384; 16-byte chunk q at q ^ (rl & 7)
     const int r8 = rl & 7;
@@ -355,6 +368,10 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(GU_BAR_ACCEMPTY + buf));   // accumulator may be overwritten
+        if (st.rowmask && (st.flags & CH_MASK_FIRST)) {
+#pragma unroll
+          for (int q = 0; q < 128; ++q) v[q] *= rm;
+        }
         if (st.res) {
           const float4* rp = reinterpret_cast<const float4*>(st.res + (size_t)(live ? m : 0) * 128);
 #pragma unroll
@@ -385,7 +402,7 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
 #pragma unroll
           for (int q = 0; q < 128; ++q) v[q] = (v[q] - mu) * rstd * __ldg(st.gamma + q) + __ldg(st.beta + q);
         }
-        if (st.rowmask) {
+        if (st.rowmask && !(st.flags & CH_MASK_FIRST)) {
 #pragma unroll
           for (int q = 0; q < 128; ++q) v[q] *= rm;
         }
@@ -414,7 +431,7 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
           }
           tc_wait_st();
         }
-        if (st.flags & CH_NEXT_A) publish_a();
+        if (st.flags & CH_NEXT_A) publish_a(0);
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;\n" ::: "memory");
         if (tma_out && tid == 0) {
@@ -430,49 +447,59 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
   } else if (warp == 4) {
     // ================================ MMA issuer ==================================================
     const uint32_t idesc = idesc_f16(128, 128);
-    int it = 0;
+    int wi = 0, ai = 0;                                       // W tile counter (ring), accumulator counter
     uint32_t a_ph = 0;
     bool a_new = true;
     for (int s = 0; s < a.nstages; ++s) {
       const int ntiles = (a.st[s].N + 127) / 128;
-      if (a_new) {                                            // the A operand was (re)written by the row threads
+      const int kchunks = s == 0 ? a.kchunks : 1;
+      if (a_new && kchunks == 1) {                            // the A operand was (re)written by the row threads
         mbar_wait(bar(GU_BAR_A), a_ph);
         a_ph ^= 1u;
         tc_fence_after();
       }
       a_new = (a.st[s].flags & CH_NEXT_A) != 0;
-      for (int nt = 0; nt < ntiles; ++nt, ++it) {
-        const int buf = it & 1;
-        const uint32_t ph = (it >> 1) & 1u;
-        mbar_wait(bar(GU_BAR_WFULL + buf), ph);
-        if (it >= 2) mbar_wait(bar(GU_BAR_ACCEMPTY + buf), ((it >> 1) - 1) & 1u);
-        tc_fence_after();
-        const uint32_t wt = sbase + GU_SM_W + buf * GU_TILE_BYTES;
-        const uint32_t d = tmem + GU_COL_ACC + 128 * buf;
+      for (int nt = 0; nt < ntiles; ++nt, ++ai) {
+        const int abuf_acc = ai & 1;
+        if (ai >= 2) mbar_wait(bar(GU_BAR_ACCEMPTY + abuf_acc), ((ai >> 1) - 1) & 1u);
+        const uint32_t d = tmem + GU_COL_ACC + 128 * abuf_acc;
+        for (int kc = 0; kc < kchunks; ++kc, ++wi) {
+          const int buf = wi & 1;
+          uint32_t acol = GU_COL_A;
+          if (kchunks > 1) {                                  // K loop: chunk kc sits in A buffer kc & 1
+            mbar_wait(bar((kc & 1) ? GU_BAR_A1 : GU_BAR_A), (kc >> 1) & 1u);
+            if (kc & 1) acol = CH_COL_RES;
+          }
+          mbar_wait(bar(GU_BAR_WFULL + buf), (wi >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t wt = sbase + GU_SM_W + buf * GU_TILE_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t dh = smem_desc(wt + ks * 4096, 2048, 128);
-          const uint64_t dl = smem_desc(wt + 32768 + ks * 4096, 2048, 128);
-          const uint32_t a_hi = tmem + GU_COL_A + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t dh = smem_desc(wt + ks * 4096, 2048, 128);
+            const uint64_t dl = smem_desc(wt + 32768 + ks * 4096, 2048, 128);
+            const uint32_t a_hi = tmem + acol + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
+            if (elect_one()) {
+              mma_cta_ts(d, a_lo, dh, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+              mma_cta_ts(d, a_hi, dl, idesc, 1u);
+              mma_cta_ts(d, a_hi, dh, idesc, 1u);
+            }
+            __syncwarp();
+          }
           if (elect_one()) {
-            mma_cta_ts(d, a_lo, dh, idesc, ks == 0 ? 0u : 1u);
-            mma_cta_ts(d, a_hi, dl, idesc, 1u);
-            mma_cta_ts(d, a_hi, dh, idesc, 1u);
+            commit_cta(bar(GU_BAR_WEMPTY + buf));
+            if (kchunks > 1) commit_cta(bar(GU_BAR_AFREE + (kc & 1)));
+            if (kc == kchunks - 1) commit_cta(bar(GU_BAR_ACCFULL + abuf_acc));
           }
           __syncwarp();
         }
-        if (elect_one()) {
-          commit_cta(bar(GU_BAR_WEMPTY + buf));
-          commit_cta(bar(GU_BAR_ACCFULL + buf));
-        }
-        __syncwarp();
       }
+      if (s == 0 && kchunks > 1) a_ph = ((kchunks + 1) >> 1) & 1u;   // phases consumed on the first A barrier
     }
   } else if (lane == 0) {
     // ================================ W producer ==================================================
     int it = 0;
     for (int s = 0; s < a.nstages; ++s) {
-      const int ntiles = (a.st[s].N + 127) / 128;
+      const int ntiles = ((a.st[s].N + 127) / 128) * (s == 0 ? a.kchunks : 1);   // K loop: one tile per chunk
       for (int nt = 0; nt < ntiles; ++nt, ++it) {
         const int buf = it & 1;
         if (it >= 2) mbar_wait(bar(GU_BAR_WEMPTY + buf), ((it >> 1) - 1) & 1u);
@@ -512,8 +539,9 @@ int launch_linear_umma(const float* x, const float* w, int ldw, const float* bia
 }
 
 // Host side of the chain: validates the layer list, encodes one tensor map per stored output, launches.
-int launch_node_chain(const float* x, int M, const NodeChainStage* stages, int n, cudaStream_t st) {
-  PF_REQUIRE(x && stages && n >= 1 && n <= CH_MAXS, PF_ERR_BAD_CONFIG);
+int launch_node_chain(const float* x, int M, const NodeChainStage* stages, int n, cudaStream_t st, int kchunks) {
+  PF_REQUIRE(x && stages && n >= 1 && n <= CH_MAXS && kchunks >= 1, PF_ERR_BAD_CONFIG);
+  PF_REQUIRE(kchunks == 1 || stages[0].N <= 128, PF_ERR_BAD_SHAPE);
   if (M == 0) return PF_OK;
   ChainArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -527,13 +555,14 @@ int launch_node_chain(const float* x, int M, const NodeChainStage* stages, int n
     ChainStage& d = a.st[s];
     d.wpack = static_cast<const uint4*>(h.wpack); d.bias = h.bias; d.res = h.res; d.gamma = h.gamma; d.beta = h.beta;
     d.rowmask = h.rowmask; d.out = h.out; d.N = h.N; d.act = h.act;
-    d.flags = (h.next_a ? CH_NEXT_A : 0) | (h.save_res ? CH_SAVE_RES : 0) | (h.res_from_chain ? CH_RES_TMEM : 0);
+    d.flags = (h.next_a ? CH_NEXT_A : 0) | (h.save_res ? CH_SAVE_RES : 0) | (h.res_from_chain ? CH_RES_TMEM : 0) |
+              (h.mask_first ? CH_MASK_FIRST : 0);
     if (h.out && (h.N & 3) == 0) {
       PF_REQUIRE(aligned16(h.out), PF_ERR_MISALIGNED);
       PF_TRY(encode_y_map(&a.tm[s], h.out, M, h.N));
     }
   }
-  a.x = x; a.M = M; a.nstages = n;
+  a.x = x; a.M = M; a.nstages = n; a.kchunks = kchunks;
   node_chain_kernel<<<(M + 127) / 128, GU_THREADS, GU_SMEM, st>>>(a);
   PF_CHECK_LAUNCH();
   return PF_OK;
