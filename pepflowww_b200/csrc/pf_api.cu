@@ -372,7 +372,7 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
     // IPA (ga.py:98-104); with chains the projection was produced by the previous chain
     if (!chains)
       PF_TRY(launch_linear(ws.s, W[PF_B_PROJ_W], W[PF_B_PROJ_B], nullptr, nullptr, ws.proj, M, 128, NPROJ, 0, st));
-    PF_TRY(launch_ipa_points(ws.proj, rot, trans, ws.pts, M, st));
+    if (opt_ipa_impl() < 3) PF_TRY(launch_ipa_points(ws.proj, rot, trans, ws.pts, M, st));   // variants 3 / 4 pack from proj
     IpaArgs ia{ws.proj, ws.pts, z, W[PF_B_LINB_W], W[PF_B_LINB_B], W[PF_B_DOWNZ_W], W[PF_B_DOWNZ_B], W[PF_B_HEAD_W],
                rot, trans, res_mask, ws.feats, B, L};
     PF_TRY(launch_ipa_attention(ia, ws.ipa_ws, ws.ipa_ws_bytes, st));

@@ -143,6 +143,191 @@ __global__ void __launch_bounds__(256) ipa_pack2_kernel(IpaPack2Args a) {
   }
 }
 
+// ---- variant 3 / 4 packer: the same blobs and Q' tiles straight from the projection and the frames.
+// The rows a CTA needs are first staged in shared memory with coalesced 16-byte loads (k | v of all heads, the
+// local-frame points), the points go to the global frame there (Rigid.apply, rigid_utils.py:1124-1136 - no separate
+// ipa_points pass, no pts buffer), and the fragments are then cut from shared memory; every HBM access is a full line.
+constexpr int P3_THREADS = 512;                  // two CTAs per SM: 32 warps to hide the shared-memory latency
+constexpr int P3_KVP = 2048 + 8;                  // padded k|v row (floats): fragment loads spread over the banks
+constexpr int P3_NP = PQ + PV;                    // 20 key / value points per head
+constexpr int P3_OFF_KV = 0;                                      // [8 keys][P3_KVP]
+constexpr int P3_OFF_LOC = P3_OFF_KV + V2_TK * P3_KVP;            // [8 keys][480] local-frame kv points (proj order)
+constexpr int P3_OFF_KP = P3_OFF_LOC + V2_TK * 480;               // [8 keys][8 h][24]  global k points [p][xyz]
+constexpr int P3_OFF_VP = P3_OFF_KP + V2_TK * H * PQ * 3;         // [8 keys][8 h][36]  global v points
+constexpr int P3_OFF_FR = P3_OFF_VP + V2_TK * H * PV * 3;         // [16 rows][12] rotation | translation
+constexpr int P3_SMEM = (P3_OFF_FR + V2_TQ * 12) * 4;
+// Q' CTA view of the same buffer: [16 rows][192] local q points at P3_OFF_LOC, [16 rows][8 h][24] global at P3_OFF_KP
+static_assert(V2_TQ * 192 <= V2_TK * 480 && V2_TQ * H * PQ * 3 <= V2_TK * H * (PQ + PV) * 3, "Q' staging fits");
+
+struct IpaPack3Args {
+  const float* proj; const float* rot; const float* trans; const float* head_w; const float* mask;
+  unsigned char* blobs; uint4* Qp;
+  int B, L, JT, IT;
+};
+
+__global__ void __launch_bounds__(P3_THREADS) ipa_pack3_kernel(IpaPack3Args a) {
+  extern __shared__ __align__(16) float p3[];
+  const int L = a.L, tid = threadIdx.x;
+  const int nblob = a.B * a.JT;
+  float* s_fr = p3 + P3_OFF_FR;
+  if ((int)blockIdx.x < nblob) {
+    const int b = blockIdx.x / a.JT, jt = blockIdx.x - b * a.JT, j0 = jt * V2_TK;
+    const size_t row0 = (size_t)b * L;
+    const int nk = min(V2_TK, L - j0);
+    float* s_kv = p3 + P3_OFF_KV;
+    float* s_loc = p3 + P3_OFF_LOC;
+    float* s_kp = p3 + P3_OFF_KP;
+    float* s_vp = p3 + P3_OFF_VP;
+    for (int i = tid; i < V2_TK * 512; i += P3_THREADS) {                    // k | v of all heads: 2048 floats per key
+      const int k = i >> 9, q = i & 511;
+      const float4 v = k < nk ? __ldg(reinterpret_cast<const float4*>(a.proj + (row0 + j0 + k) * NPROJ + OFF_KV) + q)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(s_kv + k * P3_KVP + 4 * q) = v;
+    }
+    for (int i = tid; i < V2_TK * 120; i += P3_THREADS) {                    // local kv points: 480 floats per key
+      const int k = i / 120, q = i - k * 120;
+      const float4 v = k < nk ? __ldg(reinterpret_cast<const float4*>(a.proj + (row0 + j0 + k) * NPROJ + OFF_KVP) + q)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(s_loc + k * 480 + 4 * q) = v;
+    }
+    if (tid < V2_TK * 12) {
+      const int k = tid / 12, e = tid - k * 12;
+      s_fr[tid] = k < nk ? (e < 9 ? a.rot[(row0 + j0 + k) * 9 + e] : a.trans[(row0 + j0 + k) * 3 + e - 9]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < V2_TK * H * P3_NP; i += P3_THREADS) {              // local -> global frame
+      const int k = i / (H * P3_NP), r = i - k * (H * P3_NP), h = r / P3_NP, pnt = r - h * P3_NP;
+      const float* lp = s_loc + k * 480 + h * P3_NP + pnt;            // [xyz][h][20]
+      const float lx = lp[0], ly = lp[H * P3_NP], lz = lp[2 * H * P3_NP];
+      const float* R = s_fr + k * 12;
+      float* dst = pnt < PQ ? s_kp + (k * H + h) * (PQ * 3) + pnt * 3 : s_vp + (k * H + h) * (PV * 3) + (pnt - PQ) * 3;
+      const bool on = k < nk;                                          // keys past the end stay exactly zero
+      dst[0] = on ? R[0] * lx + R[1] * ly + R[2] * lz + R[9] : 0.f;
+      dst[1] = on ? R[3] * lx + R[4] * ly + R[5] * lz + R[10] : 0.f;
+      dst[2] = on ? R[6] * lx + R[7] * ly + R[8] * lz + R[11] : 0.f;
+    }
+    __syncthreads();
+    unsigned char* blob = a.blobs + (size_t)blockIdx.x * V2_BLOB;
+#pragma unroll 5
+    for (int idx = tid; idx < H * V2_KS * 32; idx += P3_THREADS) {           // K' [h][ks][lane]
+      const int lane = idx & 31, r = idx >> 5, ks = r % V2_KS, h = r / V2_KS;
+      const int g = lane >> 2, t = lane & 3, kk = ks * 16 + 2 * t;
+      float v[4];
+      if (ks < C / 16) {
+        const float* src = s_kv + g * P3_KVP + h * 2 * C + kk;
+        const float2 x0 = *reinterpret_cast<const float2*>(src), x1 = *reinterpret_cast<const float2*>(src + 8);
+        v[0] = x0.x; v[1] = x0.y; v[2] = x1.x; v[3] = x1.y;
+      } else {
+        const float* src = s_kp + (g * H + h) * (PQ * 3);
+        const int e = kk - C;                                          // 0 .. 30, valid below 24
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ee = e + (q & 1) + (q >> 1) * 8;
+          v[q] = ee < PQ * 3 ? src[ee] : 0.f;
+        }
+      }
+      uint4 o;
+      split_pair(v[0], v[1], o.x, o.z);
+      split_pair(v[2], v[3], o.y, o.w);
+      reinterpret_cast<uint4*>(blob)[idx] = o;
+    }
+#pragma unroll 3
+    for (int idx = tid; idx < H * V2_VNT * 32; idx += P3_THREADS) {          // V' [h][nt][lane]
+      const int lane = idx & 31, r = idx >> 5, nt = r % V2_VNT, h = r / V2_VNT;
+      const int g = lane >> 2, t = lane & 3, n = nt * 8 + g, k0 = 2 * t;
+      float v0, v1;
+      if (n < C) {
+        v0 = s_kv[k0 * P3_KVP + h * 2 * C + C + n]; v1 = s_kv[(k0 + 1) * P3_KVP + h * 2 * C + C + n];
+      } else if (n < C + PV * 3) {
+        v0 = s_vp[(k0 * H + h) * (PV * 3) + n - C]; v1 = s_vp[((k0 + 1) * H + h) * (PV * 3) + n - C];
+      } else {
+        v0 = v1 = 0.f;
+      }
+      uint2 o;
+      split_pair(v0, v1, o.x, o.y);
+      reinterpret_cast<uint2*>(blob + V2_OFF_V)[idx] = o;
+    }
+    if (tid < (H + 1) * V2_TK) {                                       // key bias [h][key], key mask [key]
+      const int key = tid % V2_TK, h = tid / V2_TK, j = j0 + key;
+      float* dst = reinterpret_cast<float*>(blob + V2_OFF_KB);
+      if (h == H) {
+        dst[H * V2_TK + key] = (j < L) ? a.mask[row0 + j] : 0.f;
+      } else {
+        const float* kp = s_kp + (key * H + h) * (PQ * 3);
+        float sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < PQ * 3; ++e) sq = fmaf(kp[e], kp[e], sq);
+        dst[h * V2_TK + key] = -0.5f * a.head_w[h] * sq;
+      }
+    }
+    return;
+  }
+  // ---- Q' tile of 16 query rows [b][h][it][ks][lane]{hi, lo}
+  const int qi = blockIdx.x - nblob;
+  const int b = qi / a.IT, it = qi - b * a.IT, i0 = it * V2_TQ;
+  const size_t row0 = (size_t)b * L;
+  const int nr = min(V2_TQ, L - i0);
+  float* s_loc = p3 + P3_OFF_LOC;                                      // [16][192] local q points [xyz][h][8]
+  float* s_qp = p3 + P3_OFF_KP;                                        // [16][8 h][24] global q points
+  for (int i = tid; i < V2_TQ * 48; i += P3_THREADS) {
+    const int k = i / 48, q = i - k * 48;
+    const float4 v = k < nr ? __ldg(reinterpret_cast<const float4*>(a.proj + (row0 + i0 + k) * NPROJ + OFF_QP) + q)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(s_loc + k * 192 + 4 * q) = v;
+  }
+  if (tid < V2_TQ * 12) {
+    const int k = tid / 12, e = tid - k * 12;
+    s_fr[tid] = k < nr ? (e < 9 ? a.rot[(row0 + i0 + k) * 9 + e] : a.trans[(row0 + i0 + k) * 3 + e - 9]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < V2_TQ * H * PQ; i += P3_THREADS) {
+    const int k = i / (H * PQ), r = i - k * (H * PQ), h = r / PQ, pnt = r - h * PQ;
+    const float* lp = s_loc + k * 192 + h * PQ + pnt;
+    const float lx = lp[0], ly = lp[H * PQ], lz = lp[2 * H * PQ];
+    const float* R = s_fr + k * 12;
+    float* dst = s_qp + (k * H + h) * (PQ * 3) + pnt * 3;
+    const bool on = k < nr;
+    dst[0] = on ? R[0] * lx + R[1] * ly + R[2] * lz + R[9] : 0.f;
+    dst[1] = on ? R[3] * lx + R[4] * ly + R[5] * lz + R[10] : 0.f;
+    dst[2] = on ? R[6] * lx + R[7] * ly + R[8] * lz + R[11] : 0.f;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < H * V2_KS * 32; idx += P3_THREADS) {
+    const int lane = idx & 31, r = idx >> 5, ks = r % V2_KS, h = r / V2_KS;
+    const int g = lane >> 2, t = lane & 3, kk = ks * 16 + 2 * t;
+    const float ch = a.head_w[h];
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int k = g + half * 8;
+      if (k >= nr) continue;
+      if (ks < C / 16) {
+        const float* src = a.proj + (row0 + i0 + k) * NPROJ + OFF_Q + h * C + kk;
+        const float2 x0 = __ldg(reinterpret_cast<const float2*>(src)), x1 = __ldg(reinterpret_cast<const float2*>(src + 8));
+        v[half * 2] = x0.x * V2_QSCALE; v[half * 2 + 1] = x0.y * V2_QSCALE;
+        v[4 + half * 2] = x1.x * V2_QSCALE; v[4 + half * 2 + 1] = x1.y * V2_QSCALE;
+      } else {
+        const float* src = s_qp + (k * H + h) * (PQ * 3);
+        const int e = kk - C;
+        v[half * 2] = e < PQ * 3 ? src[e] * ch : 0.f;
+        v[half * 2 + 1] = e + 1 < PQ * 3 ? src[e + 1] * ch : 0.f;
+        v[4 + half * 2] = e + 8 < PQ * 3 ? src[e + 8] * ch : 0.f;
+        v[4 + half * 2 + 1] = e + 9 < PQ * 3 ? src[e + 9] * ch : 0.f;
+      }
+    }
+    uint4 hi, lo;
+    split_pair(v[0], v[1], hi.x, lo.x);
+    split_pair(v[2], v[3], hi.y, lo.y);
+    split_pair(v[4], v[5], hi.z, lo.z);
+    split_pair(v[6], v[7], hi.w, lo.w);
+    uint4* q = a.Qp + ((((size_t)b * H + h) * a.IT + it) * V2_KS + ks) * 64 + lane * 2;
+    q[0] = hi;
+    q[1] = lo;
+  }
+}
+
 // D(16x8, fp32) += A(16x8, fp16, row) * B(8x8, fp16, col)
 __device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
   asm volatile(
@@ -1048,8 +1233,8 @@ int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_
   const int JT = (a.L + V2_TK - 1) / V2_TK, IT = (a.L + V2_TQ - 1) / V2_TQ;
   unsigned char* blobs = static_cast<unsigned char*>(workspace);
   uint4* Qp = reinterpret_cast<uint4*>(blobs + (size_t)a.B * JT * V2_BLOB);
-  IpaPack2Args pa{a.proj, a.pts, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT};
-  ipa_pack2_kernel<<<(unsigned)(a.B * JT + a.B * IT), 256, 0, st>>>(pa);
+  IpaPack3Args pa{a.proj, a.rot, a.trans, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT};
+  ipa_pack3_kernel<<<(unsigned)(a.B * JT + a.B * IT), P3_THREADS, P3_SMEM, st>>>(pa);
   PF_CHECK_LAUNCH();
   Ipa3Args args;
   PF_TRY(encode_z_map(&args.tm_z, a.z, a.B, a.L));
@@ -1080,6 +1265,7 @@ int launch_ipa_attention_v2(const IpaArgs& a, void* workspace, size_t workspace_
 }
 
 void ipa_v2_kernels_init() {
+  cudaFuncSetAttribute(ipa_pack3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM);
   cudaFuncSetAttribute(ipa_attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM);
   cudaFuncSetAttribute(ipa_attention_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3L<false>::SMEM);
   cudaFuncSetAttribute(ipa_attention_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3L<true>::SMEM);

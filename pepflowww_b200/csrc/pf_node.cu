@@ -76,17 +76,18 @@ __global__ void add_layernorm_kernel(const float* __restrict__ a, const float* _
 // qkv row layout (torch in_proj): q(128) | k(128) | v(128), head h at columns h*32 .. h*32+31.
 //
 // Flash-style on the tensor cores (mma.sync m16n8k16, 3xFP16 split precision, fp32 accumulate): CTA = one
-// (complex, head, block of 128 query rows); K and V^T of the head are staged once per CTA in shared memory as
-// fp16 hi / lo halves in bank-conflict-free B-fragment order; each warp owns 16 query rows and streams the keys
-// in chunks of 32 with an online softmax, re-using the score fragments as the A operand of P V.
+// (complex, head); K and V^T of the head are staged ONCE in shared memory as fp16 hi / lo halves in
+// bank-conflict-free B-fragment order; the 9 warps walk the 16-row query tiles of the complex (stride 9) and stream
+// the keys in chunks of 32 with an online softmax, re-using the score fragments as the A operand of P V.
+// (One CTA per 128 query rows re-staged K / V three times at L = 271: 61 us per call.)
 constexpr int TFH = 4;
-constexpr int SEQ_ROWS = 128;    // query rows per CTA (8 warps x 16)
+constexpr int SEQ_WARPS = 9;     // 288 threads, 2 CTAs per SM
 constexpr int SEQ_KW = 20;       // words (half2) per key row of K: 16 + 4 pad  -> conflict-free fragment loads
 
 __host__ __device__ inline int seq_lp(int L) { return (L + 31) & ~31; }
 __host__ __device__ inline int seq_vw(int L) { return seq_lp(L) / 2 + 12; }   // words per d row of V^T
 
-__global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restrict__ qkv,
+__global__ void __launch_bounds__(SEQ_WARPS * 32, 2) seq_attention_kernel(const float* __restrict__ qkv,
                                                             const float* __restrict__ mask,
                                                             float* __restrict__ ctx, int L) {
   extern __shared__ __align__(16) uint32_t smem_u[];
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restr
   const float* base = qkv + (size_t)b * L * 384;
 
   // ---- stage K (row-major pairs along c) and V^T (pairs along the key index)
-  for (int idx = tid; idx < Lp * 16; idx += 256) {
+  constexpr int NT = SEQ_WARPS * 32;
+  for (int idx = tid; idx < Lp * 16; idx += NT) {
     const int j = idx >> 4, w = idx & 15;
     float2 k2 = make_float2(0.f, 0.f);
     if (j < L) k2 = *reinterpret_cast<const float2*>(base + (size_t)j * 384 + 128 + h * 32 + 2 * w);
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restr
     Kh[j * SEQ_KW + w] = hi;
     Kl[j * SEQ_KW + w] = lo;
   }
-  for (int idx = tid; idx < (Lp / 2) * 32; idx += 256) {
+  for (int idx = tid; idx < (Lp / 2) * 32; idx += NT) {
     const int d = idx & 31, jp = idx >> 5, j = 2 * jp;
     const float v0 = (j < L) ? base[(size_t)j * 384 + 256 + h * 32 + d] : 0.f;
     const float v1 = (j + 1 < L) ? base[(size_t)(j + 1) * 384 + 256 + h * 32 + d] : 0.f;
@@ -119,10 +121,11 @@ __global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restr
     Vh[d * VW + jp] = hi;
     Vl[d * VW + jp] = lo;
   }
-  for (int j = tid; j < Lp; j += 256) Ms[j] = (j < L && mask[(size_t)b * L + j] != 0.f) ? 0.f : -INFINITY;
+  for (int j = tid; j < Lp; j += NT) Ms[j] = (j < L && mask[(size_t)b * L + j] != 0.f) ? 0.f : -INFINITY;
 
+  __syncthreads();
+  for (int i0 = warp * 16; i0 < L; i0 += SEQ_WARPS * 16) {
   // ---- Q fragments of this warp's 16 rows (1/sqrt(32) folded in)
-  const int i0 = blockIdx.z * SEQ_ROWS + warp * 16;
   const int i_lo = i0 + g, i_hi = i0 + g + 8;
   uint32_t qh[2][4], ql[2][4];
   {
@@ -145,8 +148,6 @@ __global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restr
       split_pair(a3.x * scale, a3.y * scale, qh[ks][3], ql[ks][3]);
     }
   }
-  __syncthreads();
-  if (i0 >= L) return;
 
   float O[4][4];
 #pragma unroll
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(256) seq_attention_kernel(const float* __restr
     if (i_hi < L)
       *reinterpret_cast<float2*>(ctx + ((size_t)b * L + i_hi) * 128 + h * 32 + d) = make_float2(O[n][2] * il_hi, O[n][3] * il_hi);
   }
+  }   // row tiles
 }
 
 // ---------------------------------------------------------------- K7: rigid update
@@ -379,7 +381,7 @@ int launch_seq_attention(const float* qkv, const float* mask, float* ctx, int B,
   if (B == 0 || L == 0) return PF_OK;
   const size_t smem = seq_attention_smem(L);
   if (smem > 227 * 1024) return PF_ERR_BAD_SHAPE;  // L <= ~980
-  seq_attention_kernel<<<dim3(TFH, B, (L + SEQ_ROWS - 1) / SEQ_ROWS), 256, smem, st>>>(qkv, mask, ctx, L);
+  seq_attention_kernel<<<dim3(TFH, B), SEQ_WARPS * 32, smem, st>>>(qkv, mask, ctx, L);
   PF_CHECK_LAUNCH();
   return PF_OK;
 }
