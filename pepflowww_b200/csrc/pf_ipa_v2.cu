@@ -1201,29 +1201,40 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
   float* swz = reinterpret_cast<float*>(smem + LT::SM_WDZ);      // [16 d][68]
   for (int idx = tid; idx < 16 * CZ; idx += V3_THREADS) swz[(idx >> 6) * V2_ZP + (idx & 63)] = a.w_dz[idx];
   __syncthreads();
-  {
-    const int pairidx = tid >> 2, d0 = (tid & 3) * 4;   // pairidx = i * 8 + head; 4 of the 16 outputs per thread
-    const int i = pairidx >> 3, hh = pairidx & 7;
-    if (i0 + i < L) {
-      const float* src = sop + (i * H + hh) * V2_ZP;
-      float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-      for (int c = 0; c < CZ; c += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(src + c);
+  if (tid < 128) {
+    // 4 x 4 register tile per thread: pairs pq + 32 e (pair = i * 8 + head) x outputs dq + 4 e'.  Lanes of a warp read
+    // 8 consecutive pair rows / 4 consecutive W_dz rows (pitch 68: conflict-free), so the 16 FMAs of a channel cost
+    // 8 shared-memory loads per 4 channels instead of the 20 of a 1 x 4 tile - the epilogue was MIO-bound.
+    const int dq = tid & 3, pq = tid >> 2;
+    float acc[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f; }
+#pragma unroll 2
+    for (int c = 0; c < CZ; c += 4) {
+      float4 x[4], w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        x[e] = *reinterpret_cast<const float4*>(sop + (pq + 32 * e) * V2_ZP + c);
+        w[e] = *reinterpret_cast<const float4*>(swz + (dq + 4 * e) * V2_ZP + c);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-          const float4 w = *reinterpret_cast<const float4*>(swz + (d0 + d) * V2_ZP + c);
-          acc4[d] = fmaf(w.x, x.x, acc4[d]);
-          acc4[d] = fmaf(w.y, x.y, acc4[d]);
-          acc4[d] = fmaf(w.z, x.z, acc4[d]);
-          acc4[d] = fmaf(w.w, x.w, acc4[d]);
+          acc[e][d] = fmaf(w[d].x, x[e].x, acc[e][d]);
+          acc[e][d] = fmaf(w[d].y, x[e].y, acc[e][d]);
+          acc[e][d] = fmaf(w[d].z, x[e].z, acc[e][d]);
+          acc[e][d] = fmaf(w[d].w, x[e].w, acc[e][d]);
         }
-      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int pairidx = pq + 32 * e, i = pairidx >> 3, hh = pairidx & 7;
+      if (i0 + i >= L) continue;
       const float inv = sl[hh * V2_TQ + i];
-      float4 o;
-      o.x = acc4[0] * inv + a.b_dz[d0 + 0]; o.y = acc4[1] * inv + a.b_dz[d0 + 1];
-      o.z = acc4[2] * inv + a.b_dz[d0 + 2]; o.w = acc4[3] * inv + a.b_dz[d0 + 3];
-      *reinterpret_cast<float4*>(a.feats + (rowb + i0 + i) * NFEAT + 1024 + 384 + hh * 16 + d0) = o;
+      float* out = a.feats + (rowb + i0 + i) * NFEAT + 1024 + 384 + hh * 16;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) out[dq + 4 * d] = acc[e][d] * inv + a.b_dz[dq + 4 * d];
     }
   }
 }
