@@ -60,6 +60,8 @@ int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_poin
  *   "chain_impl": 1 = the K = 128 node layers between the attention kernels run as fused layer chains (one
  *                kernel per chain, activations in tensor memory; needs gemm_impl = 2 and prepacked weights;
  *                default), 0 = one GEMM / LayerNorm launch per layer
+ *   "pack_impl" : IPA operand packing for ipa_impl 3 / 4: 1 = persistent double-buffered kernel (bulk copies of the
+ *                next key tile under the conversion of the current one; default), 0 = one CTA per key tile
  */
 int pf_set_option(const char* name, int value);
 int pf_get_option(const char* name);

@@ -163,12 +163,13 @@ struct IpaPack3Args {
   const float* proj; const float* rot; const float* trans; const float* head_w; const float* mask;
   unsigned char* blobs; uint4* Qp;
   int B, L, JT, IT;
+  int q_only;                   // 1: the grid holds only the Q' tiles (the blobs come from ipa_pack4_kernel)
 };
 
 __global__ void __launch_bounds__(P3_THREADS) ipa_pack3_kernel(IpaPack3Args a) {
   extern __shared__ __align__(16) float p3[];
   const int L = a.L, tid = threadIdx.x;
-  const int nblob = a.B * a.JT;
+  const int nblob = a.q_only ? 0 : a.B * a.JT;
   float* s_fr = p3 + P3_OFF_FR;
   if ((int)blockIdx.x < nblob) {
     const int b = blockIdx.x / a.JT, jt = blockIdx.x - b * a.JT, j0 = jt * V2_TK;
@@ -267,8 +268,10 @@ __global__ void __launch_bounds__(P3_THREADS) ipa_pack3_kernel(IpaPack3Args a) {
   const int b = qi / a.IT, it = qi - b * a.IT, i0 = it * V2_TQ;
   const size_t row0 = (size_t)b * L;
   const int nr = min(V2_TQ, L - i0);
-  float* s_loc = p3 + P3_OFF_LOC;                                      // [16][192] local q points [xyz][h][8]
-  float* s_qp = p3 + P3_OFF_KP;                                        // [16][8 h][24] global q points
+  // q_only launches get a compact 25 KB layout (several CTAs per SM): local points | global points | frames
+  float* s_loc = a.q_only ? p3 : p3 + P3_OFF_LOC;                      // [16][192] local q points [xyz][h][8]
+  float* s_qp = a.q_only ? p3 + V2_TQ * 192 : p3 + P3_OFF_KP;          // [16][8 h][24] global q points
+  if (a.q_only) s_fr = p3 + 2 * V2_TQ * 192;
   for (int i = tid; i < V2_TQ * 48; i += P3_THREADS) {
     const int k = i / 48, q = i - k * 48;
     const float4 v = k < nr ? __ldg(reinterpret_cast<const float4*>(a.proj + (row0 + i0 + k) * NPROJ + OFF_QP) + q)
@@ -325,6 +328,132 @@ __global__ void __launch_bounds__(P3_THREADS) ipa_pack3_kernel(IpaPack3Args a) {
     uint4* q = a.Qp + ((((size_t)b * H + h) * a.IT + it) * V2_KS + ks) * 64 + lane * 2;
     q[0] = hi;
     q[1] = lo;
+  }
+}
+
+// ---- persistent, double-buffered blob packer ("pack_impl" = 1, default): the K' / V' part of ipa_pack3 with the
+// rows of the NEXT key tile landing in shared memory (bulk copies on an mbarrier) while the current tile is being cut
+// into fragments, one CTA per SM walking the tiles with stride gridDim.x.  The Q' tiles keep the kernel above.
+constexpr int P4_THREADS = 768;                                    // one CTA per SM: 24 warps cut fragments
+constexpr int P4_STAGE = V2_TK * P3_KVP + V2_TK * 480;            // floats per stage: k|v rows, local kv points
+constexpr int P4_OFF_KP = 2 * P4_STAGE;
+constexpr int P4_OFF_VP = P4_OFF_KP + V2_TK * H * PQ * 3;
+constexpr int P4_OFF_FR = P4_OFF_VP + V2_TK * H * PV * 3;
+constexpr int P4_OFF_BAR = P4_OFF_FR + V2_TK * 12;
+constexpr int P4_SMEM = (P4_OFF_BAR + 4) * 4;
+static_assert((P3_KVP * 4) % 16 == 0 && (P4_STAGE * 4) % 16 == 0 && (V2_TK * P3_KVP * 4) % 16 == 0, "bulk-copy alignment");
+static_assert(P4_SMEM <= 232448, "shared memory budget");
+
+__global__ void __launch_bounds__(P4_THREADS, 1) ipa_pack4_kernel(IpaPack3Args a) {
+  extern __shared__ __align__(16) float p4[];
+  const int L = a.L, tid = threadIdx.x;
+  const int nblob = a.B * a.JT;
+  float* s_kp = p4 + P4_OFF_KP;
+  float* s_vp = p4 + P4_OFF_VP;
+  float* s_fr = p4 + P4_OFF_FR;
+  const uint32_t bar0 = smem_u32(p4 + P4_OFF_BAR);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int blob, int stage) {                    // one thread: rows of key tile `blob` -> stage
+    const int b = blob / a.JT, jt = blob - b * a.JT, j0 = jt * V2_TK;
+    const int nk = min(V2_TK, L - j0);
+    const float* src = a.proj + ((size_t)b * L + j0) * NPROJ;
+    const uint32_t dkv = smem_u32(p4 + stage * P4_STAGE), dloc = dkv + V2_TK * P3_KVP * 4;
+    const uint32_t bar = bar0 + 8 * stage;
+    mbar_arrive_expect_tx(bar, nk * (2 * H * C * 4 + 480 * 4));
+    for (int k = 0; k < nk; ++k) {
+      bulk_g2s(dkv + k * P3_KVP * 4, src + (size_t)k * NPROJ + OFF_KV, 2 * H * C * 4, bar);
+      bulk_g2s(dloc + k * 480 * 4, src + (size_t)k * NPROJ + OFF_KVP, 480 * 4, bar);
+    }
+  };
+  if (tid == 0 && (int)blockIdx.x < nblob) issue(blockIdx.x, 0);
+  int n = 0;
+  for (int blob = blockIdx.x; blob < nblob; blob += gridDim.x, ++n) {
+    const int stage = n & 1;
+    const int b = blob / a.JT, jt = blob - b * a.JT, j0 = jt * V2_TK;
+    const size_t row0 = (size_t)b * L;
+    const int nk = min(V2_TK, L - j0);
+    // every thread has left the previous tile (its reads of stage ^ 1 included): refill that stage
+    if (tid == 0 && blob + (int)gridDim.x < nblob) issue(blob + gridDim.x, stage ^ 1);
+    if (tid < V2_TK * 12) {
+      const int k = tid / 12, e = tid - k * 12;
+      s_fr[tid] = k < nk ? (e < 9 ? a.rot[(row0 + j0 + k) * 9 + e] : a.trans[(row0 + j0 + k) * 3 + e - 9]) : 0.f;
+    }
+    mbar_wait_cta(bar0 + 8 * stage, (n >> 1) & 1);
+    __syncthreads();
+    const float* s_kv = p4 + stage * P4_STAGE;
+    const float* s_loc = s_kv + V2_TK * P3_KVP;
+    for (int i = tid; i < V2_TK * H * P3_NP; i += P4_THREADS) {        // local -> global frame
+      const int k = i / (H * P3_NP), r = i - k * (H * P3_NP), h = r / P3_NP, pnt = r - h * P3_NP;
+      const bool on = k < nk;                                          // keys past the end stay exactly zero
+      const float* lp = s_loc + k * 480 + h * P3_NP + pnt;            // [xyz][h][20]
+      const float lx = on ? lp[0] : 0.f, ly = on ? lp[H * P3_NP] : 0.f, lz = on ? lp[2 * H * P3_NP] : 0.f;
+      const float* R = s_fr + k * 12;
+      float* dst = pnt < PQ ? s_kp + (k * H + h) * (PQ * 3) + pnt * 3 : s_vp + (k * H + h) * (PV * 3) + (pnt - PQ) * 3;
+      dst[0] = on ? R[0] * lx + R[1] * ly + R[2] * lz + R[9] : 0.f;
+      dst[1] = on ? R[3] * lx + R[4] * ly + R[5] * lz + R[10] : 0.f;
+      dst[2] = on ? R[6] * lx + R[7] * ly + R[8] * lz + R[11] : 0.f;
+    }
+    __syncthreads();
+    unsigned char* out = a.blobs + (size_t)blob * V2_BLOB;
+#pragma unroll 5
+    for (int idx = tid; idx < H * V2_KS * 32; idx += P4_THREADS) {     // K' [h][ks][lane]
+      const int lane = idx & 31, r = idx >> 5, ks = r % V2_KS, h = r / V2_KS;
+      const int g = lane >> 2, t = lane & 3, kk = ks * 16 + 2 * t;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (g < nk) {                                                    // rows past the end were not copied
+        if (ks < C / 16) {
+          const float* src = s_kv + g * P3_KVP + h * 2 * C + kk;
+          const float2 x0 = *reinterpret_cast<const float2*>(src), x1 = *reinterpret_cast<const float2*>(src + 8);
+          v[0] = x0.x; v[1] = x0.y; v[2] = x1.x; v[3] = x1.y;
+        } else {
+          const float* src = s_kp + (g * H + h) * (PQ * 3);
+          const int e = kk - C;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int ee = e + (q & 1) + (q >> 1) * 8;
+            v[q] = ee < PQ * 3 ? src[ee] : 0.f;
+          }
+        }
+      }
+      uint4 o;
+      split_pair(v[0], v[1], o.x, o.z);
+      split_pair(v[2], v[3], o.y, o.w);
+      reinterpret_cast<uint4*>(out)[idx] = o;
+    }
+#pragma unroll 3
+    for (int idx = tid; idx < H * V2_VNT * 32; idx += P4_THREADS) {    // V' [h][nt][lane]
+      const int lane = idx & 31, r = idx >> 5, nt = r % V2_VNT, h = r / V2_VNT;
+      const int g = lane >> 2, t = lane & 3, nn = nt * 8 + g, k0 = 2 * t;
+      float v0 = 0.f, v1 = 0.f;
+      if (nn < C) {
+        if (k0 < nk) v0 = s_kv[k0 * P3_KVP + h * 2 * C + C + nn];
+        if (k0 + 1 < nk) v1 = s_kv[(k0 + 1) * P3_KVP + h * 2 * C + C + nn];
+      } else if (nn < C + PV * 3) {
+        v0 = s_vp[(k0 * H + h) * (PV * 3) + nn - C]; v1 = s_vp[((k0 + 1) * H + h) * (PV * 3) + nn - C];
+      }
+      uint2 o;
+      split_pair(v0, v1, o.x, o.y);
+      reinterpret_cast<uint2*>(out + V2_OFF_V)[idx] = o;
+    }
+    if (tid < (H + 1) * V2_TK) {                                       // key bias [h][key], key mask [key]
+      const int key = tid % V2_TK, h = tid / V2_TK, j = j0 + key;
+      float* dst = reinterpret_cast<float*>(out + V2_OFF_KB);
+      if (h == H) {
+        dst[H * V2_TK + key] = (j < L) ? a.mask[row0 + j] : 0.f;
+      } else {
+        const float* kp = s_kp + (key * H + h) * (PQ * 3);
+        float sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < PQ * 3; ++e) sq = fmaf(kp[e], kp[e], sq);
+        dst[h * V2_TK + key] = -0.5f * a.head_w[h] * sq;
+      }
+    }
+    __syncthreads();                                                   // s_kp / s_vp / s_fr / this stage are free again
   }
 }
 
@@ -1246,8 +1375,16 @@ int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_
   const int JT = (a.L + V2_TK - 1) / V2_TK, IT = (a.L + V2_TQ - 1) / V2_TQ;
   unsigned char* blobs = static_cast<unsigned char*>(workspace);
   uint4* Qp = reinterpret_cast<uint4*>(blobs + (size_t)a.B * JT * V2_BLOB);
-  IpaPack3Args pa{a.proj, a.rot, a.trans, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT};
-  ipa_pack3_kernel<<<(unsigned)(a.B * JT + a.B * IT), P3_THREADS, P3_SMEM, st>>>(pa);
+  IpaPack3Args pa{a.proj, a.rot, a.trans, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT, 0};
+  if (opt_pack_impl() == 1) {
+    const int nblob = a.B * JT;
+    ipa_pack4_kernel<<<nblob < num_sms() ? nblob : num_sms(), P4_THREADS, P4_SMEM, st>>>(pa);
+    PF_CHECK_LAUNCH();
+    pa.q_only = 1;
+    ipa_pack3_kernel<<<(unsigned)(a.B * IT), P3_THREADS, (2 * V2_TQ * 192 + V2_TQ * 12) * 4, st>>>(pa);
+  } else {
+    ipa_pack3_kernel<<<(unsigned)(a.B * JT + a.B * IT), P3_THREADS, P3_SMEM, st>>>(pa);
+  }
   PF_CHECK_LAUNCH();
   Ipa3Args args;
   PF_TRY(encode_z_map(&args.tm_z, a.z, a.B, a.L));
@@ -1279,6 +1416,7 @@ int launch_ipa_attention_v2(const IpaArgs& a, void* workspace, size_t workspace_
 
 void ipa_v2_kernels_init() {
   cudaFuncSetAttribute(ipa_pack3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM);
+  cudaFuncSetAttribute(ipa_pack4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P4_SMEM);
   cudaFuncSetAttribute(ipa_attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM);
   cudaFuncSetAttribute(ipa_attention_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3L<false>::SMEM);
   cudaFuncSetAttribute(ipa_attention_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3L<true>::SMEM);

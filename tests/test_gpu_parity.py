@@ -171,6 +171,31 @@ def test_ipa_module_golden(dev, model, tag, impl):
     assert rel_err(out.cpu()[valid], g["ipa0"][valid]) < TOL
 
 
+@pytest.mark.parametrize("shape", [(2, 30), (3, 37), (2, 271)])
+def test_ipa_pack_variants_identical(dev, model, shape):
+    """The persistent double-buffered operand packer (pack_impl = 1) and the one-CTA-per-key-tile packer write the
+    same fragments: the IPA module output is bit-identical (ragged last key / query tiles included)."""
+    from pepflowww_b200 import _lib
+    from pepflowww_b200.rigid import create_rigid
+    B, L = shape
+    gen = torch.Generator().manual_seed(L)
+    s = torch.randn(B, L, 128, generator=gen).to(dev)
+    z = torch.randn(B, L, L, 64, generator=gen).to(dev)
+    q = torch.nn.functional.normalize(torch.randn(B, L, 4, generator=gen), dim=-1)
+    from oracle import pepflow_oracle as orc
+    rig = create_rigid(orc.quat_to_rot(q).to(dev), (torch.randn(B, L, 3, generator=gen) * 8.0).to(dev))
+    m = (torch.rand(B, L, generator=gen) > 0.15).float().to(dev)
+    outs = []
+    try:
+        for pack in (0, 1):
+            _lib.set_option("pack_impl", pack)
+            with torch.no_grad():
+                outs.append(model.ga_encoder.trunk["ipa_1"](s, z, rig, m).clone())
+    finally:
+        _lib.set_option("pack_impl", 1)
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("tag", ["ga_encoder_a", "ga_encoder_b"])
 def test_edge_and_node_transition_golden(dev, model, tag, impl):
     g = load_golden(tag)
