@@ -229,6 +229,16 @@ int pf_edge_embed(const int64_t* aa, const int64_t* res_nb, const int64_t* chain
                   const float* bo2, const float* wo3_t, const float* bo3, float* out, int N, int L, int atoms_in,
                   void* stream);
 
+/* NodeEmbedder.forward, models_con/node.py:35-105, fused: local-frame coordinates placed
+ * in the residue type's slot, backbone-dihedral encodings, 4-layer MLP, CA mask.  Inputs as pf_edge_embed.  Constants:
+ * t1[22,256] = aatype_embed W1[:, 0:128]^T + b1; w1c_t[990,256] = W1[:, 128:1118]^T; w1d_t[39,256] = W1[:, 1118:1157]^T;
+ * w2_t[256,128], w3_t[128,128], w4_t[128,128] transposed mlp.2 / mlp.4 / mlp.6 weights, b2 / b3 / b4 their biases.
+ * out[N,L,128]. */
+int pf_node_embed(const int64_t* aa, const int64_t* res_nb, const int64_t* chain_nb, const float* pos_atoms,
+                  const uint8_t* mask_atoms, const uint8_t* structure_mask, const float* t1, const float* w1c_t,
+                  const float* w1d_t, const float* w2_t, const float* b2, const float* w3_t, const float* b3,
+                  const float* w4_t, const float* b4, float* out, int N, int L, int atoms_in, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

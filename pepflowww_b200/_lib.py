@@ -55,6 +55,7 @@ SIGNATURES = {
     "pf_ga_encoder_workspace_bytes": (_sz, [_i, _i]),
     "pf_ga_encoder_forward": (_i, [_p] * 15 + [_sz] + [_i] * 2 + [_p]),
     "pf_edge_embed": (_i, [_p] * 21 + [_i] * 3 + [_p]),
+    "pf_node_embed": (_i, [_p] * 16 + [_i] * 3 + [_p]),
 }
 
 # enum sizes of include/pepflow_b200.h

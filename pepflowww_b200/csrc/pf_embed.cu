@@ -247,3 +247,195 @@ extern "C" int pf_edge_embed(const int64_t* aa, const int64_t* res_nb, const int
   PF_CHECK_LAUNCH();
   return PF_OK;
 }
+
+// =================================================================================================
+// Once-per-sample residue embedder: NodeEmbedder.forward, models_con/node.py:35-105.
+//   crd  = R_i^T (x_ia - CA_i) of the 15 kept atoms in the residue's own frame (geometry.py:89-111, 136-155), placed in
+//          the 45-wide slot of the residue's amino-acid type inside a 22 x 45 feature - i.e. only 45 columns of the
+//          first Linear matter, W1[:, 128 + aa * 45 ...]
+//   dih  = AngularEncoding of the backbone omega / phi / psi with their terminus masks (geometry.py:355-390)
+//   y    = MLP(1157 -> 256 -> 128 -> 128 -> 128) of [aatype_embed[aa] | crd slot | dih], times the CA mask
+// The embedding lookup is pushed through the first layer on the host (T1 = aatype_embed W1[:, :128]^T + b1); all
+// weight matrices arrive transposed so that thread n reads column n with unit stride.  A CTA embeds NE_R residues
+// so every weight element it fetches from L2 is used NE_R times.
+namespace pf {
+
+constexpr int NE_R = 8;          // residues per CTA
+constexpr int NE_T = 256;        // threads = width of the first hidden layer
+
+struct NodeEmbedArgs {
+  const int64_t* aa; const int64_t* res_nb; const int64_t* chain_nb;
+  const float* pos; const uint8_t* mask; const uint8_t* smask;
+  const float* t1;      // [22, 256]
+  const float* w1c;     // [22 * 45, 256]
+  const float* w1d;     // [39, 256]
+  const float* w2t; const float* b2;   // [256, 128]
+  const float* w3t; const float* b3;   // [128, 128]
+  const float* w4t; const float* b4;   // [128, 128]
+  float* out;           // [N, L, 128]
+  int N, L, A_in;
+};
+
+__global__ void __launch_bounds__(NE_T) node_embed_kernel(NodeEmbedArgs a) {
+  __shared__ float s_feat[NE_R][84];      // 45 local coordinates | 39 dihedral features
+  __shared__ int s_aa[NE_R];
+  __shared__ float s_mres[NE_R];
+  __shared__ float s_y1[NE_R][256];
+  __shared__ float s_y2[NE_R][128];
+  __shared__ float s_y3[NE_R][128];
+  const int tid = threadIdx.x, L = a.L, M = a.N * L;
+  const int r0 = blockIdx.x * NE_R;
+  // ---- features: thread (r, e) for e < 45 coordinates / 3 dihedrals
+  for (int i = tid; i < NE_R * 48; i += NE_T) {
+    const int r = i / 48, e = i - r * 48, row = r0 + r;
+    if (row >= M) {                                              // ragged last CTA: inert rows
+      if (e < 45) s_feat[r][e] = 0.f;
+      else for (int q = 0; q < 13; ++q) s_feat[r][45 + (e - 45) * 13 + q] = 0.f;
+      if (e == 0) { s_aa[r] = 0; s_mres[r] = 0.f; }
+      continue;
+    }
+    const int j = row % L;
+    const float* P = a.pos + (size_t)row * a.A_in * 3;
+    const uint8_t* mk = a.mask + (size_t)row * a.A_in;
+    const bool sm = a.smask ? a.smask[row] != 0 : true;
+    if (e < 45) {
+      const int at = e / 3, c = e - at * 3;
+      // construct_3d_basis(CA, C, N): e1 along CA->C, e2 = CA->N orthogonalised, e3 = e1 x e2  (eps 1e-6 as the reference)
+      const float cx = P[3], cy = P[4], cz = P[5];
+      float ax = P[6] - cx, ay = P[7] - cy, az = P[8] - cz;
+      float inv = 1.0f / (sqrtf(ax * ax + ay * ay + az * az) + 1e-6f);
+      ax *= inv; ay *= inv; az *= inv;
+      float bx = P[0] - cx, by = P[1] - cy, bz = P[2] - cz;
+      const float d = ax * bx + ay * by + az * bz;
+      bx -= d * ax; by -= d * ay; bz -= d * az;
+      inv = 1.0f / (sqrtf(bx * bx + by * by + bz * bz) + 1e-6f);
+      bx *= inv; by *= inv; bz *= inv;
+      const float ex = ay * bz - az * by, ey = az * bx - ax * bz, ez = ax * by - ay * bx;
+      const float qx = P[3 * at] - cx, qy = P[3 * at + 1] - cy, qz = P[3 * at + 2] - cz;
+      const float v = c == 0 ? ax * qx + ay * qy + az * qz : (c == 1 ? bx * qx + by * qy + bz * qz : ex * qx + ey * qy + ez * qz);
+      s_feat[r][e] = (mk[at] && sm) ? v : 0.f;
+      if (e == 0) { s_aa[r] = (int)a.aa[row]; s_mres[r] = mk[1] ? 1.f : 0.f; }
+    } else {
+      const int which = e - 45;                                  // 0 omega, 1 phi, 2 psi
+      const int64_t rn = a.res_nb[row], cn = a.chain_nb[row];
+      bool on;                                                    // terminus masks, topology.py:5-24
+      float ang = 0.f;
+      if (which < 2) {
+        on = j > 0;
+        if (on) {
+          const int64_t dr = rn - a.res_nb[row - 1];
+          on = (dr == 1 || dr == -1) && cn == a.chain_nb[row - 1] && a.mask[(size_t)(row - 1) * a.A_in + 1] != 0;
+          const float* Q = P - (size_t)a.A_in * 3;               // residue j - 1
+          ang = which == 0 ? ee_dihedral(Q + 3, Q + 6, P, P + 3) : ee_dihedral(Q + 6, P, P + 3, P + 6);
+        }
+      } else {
+        on = j < L - 1;
+        if (on) {
+          const int64_t dr = a.res_nb[row + 1] - rn;
+          on = (dr == 1 || dr == -1) && cn == a.chain_nb[row + 1] && mk[1] != 0;
+          ang = ee_dihedral(P, P + 3, P + 6, P + (size_t)a.A_in * 3);
+        }
+      }
+      // structure mask of the residue and both neighbours, with torch.roll's wrap-around (node.py:90-96)
+      bool dm = true;
+      if (a.smask) {
+        const size_t base = (size_t)(row - j);
+        dm = sm && a.smask[base + (j + L - 1) % L] != 0 && a.smask[base + (j + 1) % L] != 0;
+      }
+      const float keep = (on && dm) ? 1.f : 0.f;
+      ang = on ? ang : 0.f;
+      float* f = &s_feat[r][45 + which * 13];
+      const float fr[6] = {1.f, 2.f, 3.f, 1.f, 1.f / 2.f, 1.f / 3.f};
+      f[0] = ang * keep;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        float sv, cv;
+        sincosf(ang * fr[q], &sv, &cv);
+        f[1 + q] = sv * keep;
+        f[7 + q] = cv * keep;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- layer 1 (212 effective inputs -> 256), ReLU: thread = output column
+  {
+    float acc[NE_R];
+#pragma unroll
+    for (int r = 0; r < NE_R; ++r) acc[r] = a.t1[s_aa[r] * 256 + tid];
+    for (int k = 0; k < 45; ++k) {
+#pragma unroll
+      for (int r = 0; r < NE_R; ++r) acc[r] = fmaf(s_feat[r][k], a.w1c[(size_t)(s_aa[r] * 45 + k) * 256 + tid], acc[r]);
+    }
+    for (int k = 0; k < 39; ++k) {
+      const float w = a.w1d[k * 256 + tid];
+#pragma unroll
+      for (int r = 0; r < NE_R; ++r) acc[r] = fmaf(s_feat[r][45 + k], w, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < NE_R; ++r) s_y1[r][tid] = fmaxf(acc[r], 0.f);
+  }
+  __syncthreads();
+  // ---- layers 2-4: 128 output columns; the two thread halves take four residues each
+  const int col = tid & 127, rb = (tid >> 7) * (NE_R / 2);
+  {
+    float acc[NE_R / 2];
+#pragma unroll
+    for (int r = 0; r < NE_R / 2; ++r) acc[r] = a.b2[col];
+    for (int k = 0; k < 256; ++k) {
+      const float w = a.w2t[k * 128 + col];
+#pragma unroll
+      for (int r = 0; r < NE_R / 2; ++r) acc[r] = fmaf(s_y1[rb + r][k], w, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < NE_R / 2; ++r) s_y2[rb + r][col] = fmaxf(acc[r], 0.f);
+  }
+  __syncthreads();
+  {
+    float acc[NE_R / 2];
+#pragma unroll
+    for (int r = 0; r < NE_R / 2; ++r) acc[r] = a.b3[col];
+    for (int k = 0; k < 128; ++k) {
+      const float w = a.w3t[k * 128 + col];
+#pragma unroll
+      for (int r = 0; r < NE_R / 2; ++r) acc[r] = fmaf(s_y2[rb + r][k], w, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < NE_R / 2; ++r) s_y3[rb + r][col] = fmaxf(acc[r], 0.f);
+  }
+  __syncthreads();
+  {
+    float acc[NE_R / 2];
+#pragma unroll
+    for (int r = 0; r < NE_R / 2; ++r) acc[r] = a.b4[col];
+    for (int k = 0; k < 128; ++k) {
+      const float w = a.w4t[k * 128 + col];
+#pragma unroll
+      for (int r = 0; r < NE_R / 2; ++r) acc[r] = fmaf(s_y3[rb + r][k], w, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < NE_R / 2; ++r) {
+      const int row = r0 + rb + r;
+      if (row < M) a.out[(size_t)row * 128 + col] = acc[r] * s_mres[rb + r];
+    }
+  }
+}
+
+}  // namespace pf
+
+extern "C" int pf_node_embed(const int64_t* aa, const int64_t* res_nb, const int64_t* chain_nb, const float* pos_atoms,
+                             const uint8_t* mask_atoms, const uint8_t* structure_mask, const float* t1,
+                             const float* w1c_t, const float* w1d_t, const float* w2_t, const float* b2,
+                             const float* w3_t, const float* b3, const float* w4_t, const float* b4, float* out,
+                             int N, int L, int atoms_in, void* stream) {
+  using namespace pf;
+  PF_REQUIRE(aa && res_nb && chain_nb && pos_atoms && mask_atoms && t1 && w1c_t && w1d_t && w2_t && b2 && w3_t && b3 &&
+                 w4_t && b4 && out, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(N >= 0 && L >= 0 && atoms_in >= EE_A, PF_ERR_BAD_SHAPE);
+  if (N == 0 || L == 0) return PF_OK;
+  NodeEmbedArgs a{aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, t1, w1c_t, w1d_t, w2_t, b2, w3_t, b3,
+                  w4_t, b4, out, N, L, atoms_in};
+  const long long rows = (long long)N * L;
+  node_embed_kernel<<<(unsigned)((rows + NE_R - 1) / NE_R), NE_T, 0, as_stream(stream)>>>(a);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}

@@ -1,5 +1,6 @@
 """NodeEmbedder (reference: models_con/node.py:11-105): once per sample; same parameter names/shapes.
-PyTorch ops on the batch's device - SURVEY section 8(f) rank 2 ("next" row), not the per-step hot path."""
+SURVEY section 8(f) rank 2.  On a CUDA device without autograd (sampling) the module is ONE fused kernel
+(pf_node_embed, csrc/pf_embed.cu); with autograd or on CPU tensors the reference formulation below runs as torch ops."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -19,9 +20,26 @@ class NodeEmbedder(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(infeat, feat_dim * 2), nn.ReLU(), nn.Linear(feat_dim * 2, feat_dim), nn.ReLU(),
                                  nn.Linear(feat_dim, feat_dim), nn.ReLU(), nn.Linear(feat_dim, feat_dim))
 
+    def _kernel_constants(self):
+        """Constants of pf_node_embed in prototype order (the embedding lookup pushed through the first layer)."""
+        F_ = self.feat_dim
+        l0, l2, l4, l6 = self.mlp[0], self.mlp[2], self.mlp[4], self.mlp[6]
+        w = l0.weight
+        nc = self.max_aa_types * self.max_num_atoms * 3
+        return (self.aatype_embed.weight @ w[:, :F_].t() + l0.bias, w[:, F_:F_ + nc].t().contiguous(),
+                w[:, F_ + nc:].t().contiguous(), l2.weight.t().contiguous(), l2.bias, l4.weight.t().contiguous(), l4.bias,
+                l6.weight.t().contiguous(), l6.bias)
+
     def forward(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask=None, sequence_mask=None):
         N, L = aa.size()
         A = self.max_num_atoms
+        fused = (pos_atoms.is_cuda and not torch.is_grad_enabled() and A == 15 and self.max_aa_types == 22 and
+                 self.feat_dim == 128 and self.dihed_embed.num_funcs == 3 and pos_atoms.shape[2] >= 15)
+        if fused:
+            from . import ops
+            if sequence_mask is not None:
+                aa = torch.where(sequence_mask, aa, torch.full_like(aa, fill_value=int(AA.UNK)))
+            return ops.node_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, self._kernel_constants())
         mask_residue = mask_atoms[:, :, BBHeavyAtom.CA]
         pos_atoms, mask_atoms = pos_atoms[:, :, :A], mask_atoms[:, :, :A]
         if sequence_mask is not None:

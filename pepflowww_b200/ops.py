@@ -234,3 +234,19 @@ def edge_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, cons
                             ptr(m, U8), ptr(sm, U8, allow_none=True), *[ptr(c) for c in cs], ptr(out), N, L,
                             pos.shape[2], stream()))
     return out
+
+
+def node_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, consts):
+    """NodeEmbedder.forward (models_con/node.py:35-105) as one fused kernel (pf_node_embed); `consts` in the order of
+    the C prototype (NodeEmbedder._kernel_constants)."""
+    lib = _lib.lib_for(pos_atoms.device)
+    N, L = aa.shape
+    pos = _c(pos_atoms)
+    m = _c(mask_atoms, torch.bool).view(U8)
+    sm = _c(structure_mask, torch.bool).view(U8) if structure_mask is not None else None
+    out = torch.empty(N, L, 128, device=pos.device, dtype=F32)
+    cs = [_c(c) for c in consts]
+    check(lib.pf_node_embed(ptr(_c(aa, I64), I64), ptr(_c(res_nb, I64), I64), ptr(_c(chain_nb, I64), I64), ptr(pos),
+                            ptr(m, U8), ptr(sm, U8, allow_none=True), *[ptr(c) for c in cs], ptr(out), N, L,
+                            pos.shape[2], stream()))
+    return out

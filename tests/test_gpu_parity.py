@@ -451,6 +451,38 @@ def test_embedders_on_gpu(dev, model):
     print("embedder gpu-vs-cpu: node %.2e edge %.2e" % (rel_err(enc[4].cpu(), g["node_embed"]), rel_err(enc[5].cpu(), g["edge_embed"])))
 
 
+def test_node_embed_kernel(dev, model, state_dict):
+    """pf_node_embed (fused NodeEmbedder) against the reference's output (golden fixture),
+    the oracle on a padded batch with hidden structure / sequence, and the torch formulation at the bench residue
+    count.  The backbone dihedrals of consecutive residues are well conditioned, so 1e-4 holds everywhere."""
+    from oracle import pepflow_oracle as orc
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    from pepflowww_b200.utils import recursive_to
+    keys = ("aa", "res_nb", "chain_nb", "pos_heavyatom", "mask_heavyatom")
+    g = load_golden("encode")
+    ctx = g["mask_heavyatom"][:, :, 1] & ~g["generate_mask"]
+    with torch.no_grad():
+        out = model.node_embedder(*[g[k].to(dev) for k in keys], structure_mask=ctx.to(dev), sequence_mask=ctx.to(dev))
+    e_gold = rel_err(out.cpu(), g["node_embed"])
+    batch = synthetic_batch(3, 20, 5, seed=11, eight=True)            # L = 25 padded to 32
+    ctx = batch["mask_heavyatom"][:, :, 1] & ~batch["generate_mask"]
+    with torch.no_grad():
+        out = model.node_embedder(*[batch[k].to(dev) for k in keys], structure_mask=ctx.to(dev), sequence_mask=ctx.to(dev))
+        out_nomask = model.node_embedder(*[batch[k].to(dev) for k in keys])
+    e_pad = rel_err(out.cpu(), orc.node_embedder(state_dict, *[batch[k] for k in keys], ctx, ctx))
+    e_nomask = rel_err(out_nomask.cpu(), orc.node_embedder(state_dict, *[batch[k] for k in keys], None, None))
+    assert (out.cpu()[~batch["res_mask"]] == 0).all()
+    big = recursive_to(synthetic_batch(2, 256, 15, seed=4), dev)
+    ctx = big["mask_heavyatom"][:, :, 1] & ~big["generate_mask"]
+    with torch.no_grad():
+        fused = model.node_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx)
+    with torch.enable_grad():
+        torch_path = model.node_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx).detach()
+    e_big = rel_err(fused, torch_path)
+    print("node_embed kernel: golden %.2e padded %.2e no-mask %.2e L=271 vs torch ops %.2e" % (e_gold, e_pad, e_nomask, e_big))
+    assert max(e_gold, e_pad, e_nomask, e_big) < TOL
+
+
 def _well_conditioned_pairs(pos, margin=0.05):
     """Pairs whose inter-residue dihedrals (geometry.py:393-418) stay `margin` rad away from 0 and pi: the reference
     takes acos() of a clamped cosine, whose derivative 1 / sin(theta) amplifies fp32 rounding without bound there."""
