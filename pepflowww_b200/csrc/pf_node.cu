@@ -186,13 +186,13 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, 2) seq_attention_kernel(const 
     const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
     // rows whose keys so far are all masked keep m = -inf: use 0 as the reference point (every p becomes 0)
     const float rf_lo = (mn_lo == -INFINITY) ? 0.f : mn_lo, rf_hi = (mn_hi == -INFINITY) ? 0.f : mn_hi;
-    const float al_lo = expf(m_lo - rf_lo), al_hi = expf(m_hi - rf_hi);
+    const float al_lo = __expf(m_lo - rf_lo), al_hi = __expf(m_hi - rf_hi);   // ex2.approx: ~3e-6 relative over a row
     m_lo = mn_lo; m_hi = mn_hi;
     float ps_lo = 0.f, ps_hi = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      S[nt][0] = expf(S[nt][0] - rf_lo); S[nt][1] = expf(S[nt][1] - rf_lo);
-      S[nt][2] = expf(S[nt][2] - rf_hi); S[nt][3] = expf(S[nt][3] - rf_hi);
+      S[nt][0] = __expf(S[nt][0] - rf_lo); S[nt][1] = __expf(S[nt][1] - rf_lo);
+      S[nt][2] = __expf(S[nt][2] - rf_hi); S[nt][3] = __expf(S[nt][3] - rf_hi);
       ps_lo += S[nt][0] + S[nt][1];
       ps_hi += S[nt][2] + S[nt][3];
     }
