@@ -73,7 +73,7 @@ static GaWorkspace carve(void* base, int B, int L) {
     off += al(bytes);
     return r;
   };
-  w.xmix = take(M * NMIX * 4);
+  w.xmix = take(M * NMIXP * 4);
   w.s = take(M * 128 * 4);
   w.ta = take(M * 128 * 4);
   w.tb = take(M * 128 * 4);
@@ -117,8 +117,12 @@ static size_t enumerate_packables(const pf_ga_weights* w, std::vector<PackItem>*
     off += al(gemm_umma_pack_bytes(N));
   };
   lin(w->g[PF_G_MIX2_W], 128);
+  if (w->g[PF_G_MIX0_W]) {                             // feature-mix layer [128, 629]: one tile per 128-column chunk
+    if (items) items->push_back(PackItem{w->g[PF_G_MIX0_W], 128, off, false, nullptr, nullptr, 4, -1});
+    off += al((NMIXP / 128) * gemm_umma_pack_bytes(128));
+  }
   lin(w->g[PF_G_SEQNET0_W], 128); lin(w->g[PF_G_SEQNET2_W], 128); lin(w->g[PF_G_SEQNET4_W], 20);
-  lin(w->g[PF_G_ANGNET0_W], 128); lin(w->g[PF_G_ANGNET2_W], 128);
+  lin(w->g[PF_G_ANGNET0_W], 128); lin(w->g[PF_G_ANGNET2_W], 128); lin(w->g[PF_G_ANGNET4_W], 5);
   for (int b = 0; b < w->num_blocks; ++b) {
     const float* const* W = w->blk[b];
     lin(W[PF_B_PROJ_W], NPROJ);
@@ -176,6 +180,11 @@ int pf_ga_prepack(const pf_ga_weights* w, void* buffer, size_t buffer_bytes, voi
       for (int q = 0; q < 4; ++q)
         PF_TRY(launch_gemm_umma_pack(wc + (size_t)TERMS_ROW[q] * 128, 128, TERMS_N[q],
                                      base + it.off + TERMS_TILES + TERMS_TILE0[q] * gemm_umma_pack_bytes(128), st));
+    } else if (it.kind == 4) {
+      for (int kc = 0; kc < NMIXP / 128; ++kc) {
+        const int kvalid = NMIX - kc * 128 < 128 ? NMIX - kc * 128 : 128;
+        PF_TRY(launch_gemm_umma_pack(it.w + kc * 128, NMIX, 128, base + it.off + kc * gemm_umma_pack_bytes(128), st, kvalid));
+      }
     } else if (it.kind == 3) {
       for (int kc = 0; kc < NFEAT / 128; ++kc)
         PF_TRY(launch_gemm_umma_pack(it.w + kc * 128, NFEAT, 128, base + it.off + kc * gemm_umma_pack_bytes(128), st));
@@ -331,12 +340,13 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
                             pre);
   };
 
-  // K1: feature mix (ga.py:94-95)
-  PF_TRY(launch_mix_features(node_embed, w->g[PF_G_SEQ_EMB], seqs_t, t, w->g[PF_G_TIME_FREQS], angles_t,
-                             w->g[PF_G_ANG_FREQS], ws.xmix, B, L, st));
-  PF_TRY(launch_linear(ws.xmix, w->g[PF_G_MIX0_W], w->g[PF_G_MIX0_B], nullptr, nullptr, ws.ta, M, NMIX, 128, 1, st));
   // Fused layer chains (chain_impl = 1): need the tcgen05 GEMM and the prepacked weight images of every layer
   const bool chains = opt_chain_impl() == 1 && opt_gemm_impl() == 2 && !packed.empty();
+  // K1: feature mix (ga.py:94-95); with chains the rows are zero-padded to 5 x 128 columns for the chain's K loop
+  PF_TRY(launch_mix_features(node_embed, w->g[PF_G_SEQ_EMB], seqs_t, t, w->g[PF_G_TIME_FREQS], angles_t,
+                             w->g[PF_G_ANG_FREQS], ws.xmix, B, L, st, chains ? NMIXP : NMIX));
+  if (!chains)
+    PF_TRY(launch_linear(ws.xmix, w->g[PF_G_MIX0_W], w->g[PF_G_MIX0_B], nullptr, nullptr, ws.ta, M, NMIX, 128, 1, st));
   auto stage = [&](const float* wt, const float* bias, int N, int act) {
     NodeChainStage c{};
     c.wpack = find_packed(wt, false); c.bias = bias; c.N = N; c.act = act;
@@ -352,14 +362,18 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
     return c;
   };
   if (chains) {
-    // mix2 (+ mask) -> s, then block 0's IPA projection from the same rows
+    // mix0 (K = 629 as a 5-chunk K loop) + ReLU, mix2 (+ mask) -> s, then block 0's IPA projection from the same rows
     std::vector<NodeChainStage> c;
+    NodeChainStage m0 = stage(w->g[PF_G_MIX0_W], w->g[PF_G_MIX0_B], 128, 1);
+    m0.next_a = true;
+    c.push_back(m0);
     NodeChainStage m2 = stage(w->g[PF_G_MIX2_W], w->g[PF_G_MIX2_B], 128, 0);
     m2.rowmask = res_mask; m2.out = ws.s; m2.next_a = true;
     c.push_back(m2);
     PF_REQUIRE(w->blk[0][PF_B_PROJ_W], PF_ERR_NULL_POINTER);
     c.push_back(proj_stage(0));
-    PF_TRY(run_chain(ws.ta, c));
+    for (const NodeChainStage& q : c) PF_REQUIRE(q.wpack, PF_ERR_BAD_CONFIG);
+    PF_TRY(launch_node_chain(ws.xmix, M, c.data(), (int)c.size(), st, NMIXP / 128));
   } else {
     PF_TRY(launch_linear(ws.ta, w->g[PF_G_MIX2_W], w->g[PF_G_MIX2_B], nullptr, res_mask, ws.s, M, 128, 128, 0, st));
   }
@@ -497,13 +511,29 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
       z = ws.zbuf;
     }
   }
-  // heads (ga.py:121-125)
-  PF_TRY(launch_linear(ws.s, w->g[PF_G_SEQNET0_W], w->g[PF_G_SEQNET0_B], nullptr, nullptr, ws.ta, M, 128, 128, 1, st));
-  PF_TRY(launch_linear(ws.ta, w->g[PF_G_SEQNET2_W], w->g[PF_G_SEQNET2_B], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));
-  PF_TRY(launch_linear(ws.tb, w->g[PF_G_SEQNET4_W], w->g[PF_G_SEQNET4_B], nullptr, nullptr, logits, M, 128, 20, 0, st));
-  PF_TRY(launch_linear(ws.s, w->g[PF_G_ANGNET0_W], w->g[PF_G_ANGNET0_B], nullptr, nullptr, ws.ta, M, 128, 128, 1, st));
-  PF_TRY(launch_linear(ws.ta, w->g[PF_G_ANGNET2_W], w->g[PF_G_ANGNET2_B], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));
-  PF_TRY(launch_linear(ws.tb, w->g[PF_G_ANGNET4_W], w->g[PF_G_ANGNET4_B], nullptr, nullptr, ws.ang_raw, M, 128, 5, 0, st));
+  // heads (ga.py:121-125): two three-layer chains from the final s, or one launch per layer
+  if (chains && find_packed(w->g[PF_G_ANGNET4_W], false)) {
+    const int wo[2][3] = {{PF_G_SEQNET0_W, PF_G_SEQNET2_W, PF_G_SEQNET4_W}, {PF_G_ANGNET0_W, PF_G_ANGNET2_W, PF_G_ANGNET4_W}};
+    float* dst[2] = {logits, ws.ang_raw};
+    const int width[2] = {20, 5};
+    for (int hd = 0; hd < 2; ++hd) {
+      std::vector<NodeChainStage> c;
+      NodeChainStage q = stage(w->g[wo[hd][0]], w->g[wo[hd][0] + 1], 128, 1); q.next_a = true;
+      c.push_back(q);
+      q = stage(w->g[wo[hd][1]], w->g[wo[hd][1] + 1], 128, 1); q.next_a = true;
+      c.push_back(q);
+      q = stage(w->g[wo[hd][2]], w->g[wo[hd][2] + 1], width[hd], 0); q.out = dst[hd];
+      c.push_back(q);
+      PF_TRY(run_chain(ws.s, c));
+    }
+  } else {
+    PF_TRY(launch_linear(ws.s, w->g[PF_G_SEQNET0_W], w->g[PF_G_SEQNET0_B], nullptr, nullptr, ws.ta, M, 128, 128, 1, st));
+    PF_TRY(launch_linear(ws.ta, w->g[PF_G_SEQNET2_W], w->g[PF_G_SEQNET2_B], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));
+    PF_TRY(launch_linear(ws.tb, w->g[PF_G_SEQNET4_W], w->g[PF_G_SEQNET4_B], nullptr, nullptr, logits, M, 128, 20, 0, st));
+    PF_TRY(launch_linear(ws.s, w->g[PF_G_ANGNET0_W], w->g[PF_G_ANGNET0_B], nullptr, nullptr, ws.ta, M, 128, 128, 1, st));
+    PF_TRY(launch_linear(ws.ta, w->g[PF_G_ANGNET2_W], w->g[PF_G_ANGNET2_B], nullptr, nullptr, ws.tb, M, 128, 128, 1, st));
+    PF_TRY(launch_linear(ws.tb, w->g[PF_G_ANGNET4_W], w->g[PF_G_ANGNET4_B], nullptr, nullptr, ws.ang_raw, M, 128, 5, 0, st));
+  }
   PF_TRY(launch_mod_2pi(ws.ang_raw, pred_angles, M * 5, st));
   if (node_out) {
     cudaError_t e = cudaMemcpyAsync(node_out, ws.s, (size_t)M * 128 * 4, cudaMemcpyDeviceToDevice, st);

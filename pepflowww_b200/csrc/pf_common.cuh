@@ -101,7 +101,8 @@ struct IpaArgs {
 int launch_linear(const float* x, const float* w, const float* bias, const float* residual, const float* rowmask,
                   float* y, int M, int K, int N, int act, cudaStream_t st);
 size_t gemm_umma_pack_bytes(int N);
-int launch_gemm_umma_pack(const float* w, int ldw, int N, void* wpack, cudaStream_t st);
+// kvalid: columns of w that exist from w[0] on (< 128 for the ragged last chunk of a K loop; the rest packs as zero)
+int launch_gemm_umma_pack(const float* w, int ldw, int N, void* wpack, cudaStream_t st, int kvalid = 128);
 int launch_linear_umma(const float* x, const float* w, int ldw, const float* bias, const float* rowmask, float* y,
                        int M, int N, int act, const void* wpack, bool prepacked, cudaStream_t st);
 void gemm_umma_init();
@@ -131,7 +132,9 @@ bool linear_umma_eligible(int K, int N, bool has_residual);
 int launch_linear_ld(const float* x, const float* w, int ldw, const float* bias, float* y, int M, int K, int N,
                      cudaStream_t st);
 int launch_mix_features(const float* node, const float* emb, const int64_t* seqs, const float* t, const float* tfreq,
-                        const float* angles, const float* afreq, float* x, int B, int L, cudaStream_t st);
+                        const float* angles, const float* afreq, float* x, int B, int L, cudaStream_t st,
+                        int ldx = NMIX);
+constexpr int NMIXP = 640;  // NMIX rounded up to whole 128-column chunks
 int launch_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, const float* rowmask,
                          float* y, int M, int N, cudaStream_t st);
 int launch_seq_attention(const float* qkv, const float* mask, float* ctx, int B, int L, cudaStream_t st);

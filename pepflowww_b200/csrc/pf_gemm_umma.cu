@@ -36,7 +36,7 @@ static_assert(GU_SM_OUT % 1024 == 0 && GU_SMEM <= 232448, "shared memory layout"
 constexpr uint32_t GU_COL_A = 0, GU_COL_ACC = 128;   // A: 4 chunks x (16 hi + 16 lo) columns; accumulators 2 x 128
 
 // W [N, K=128] (row stride ldw) -> tiles of 128 rows: hi [kc][n][8 halves] | lo, zero rows beyond N
-__global__ void gemm_umma_pack_kernel(const float* __restrict__ w, int ldw, int N, uint4* __restrict__ out) {
+__global__ void gemm_umma_pack_kernel(const float* __restrict__ w, int ldw, int N, uint4* __restrict__ out, int kvalid) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte unit of the hi part
   const int ntiles = (N + 127) / 128;
   if (idx >= ntiles * 2048) return;
@@ -45,7 +45,10 @@ __global__ void gemm_umma_pack_kernel(const float* __restrict__ w, int ldw, int 
   if (n < N) {
     const float* src = w + (size_t)n * ldw + kc * 8;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) split_pair(src[2 * q], src[2 * q + 1], hi[q], lo[q]);
+    for (int q = 0; q < 4; ++q) {
+      const int k = kc * 8 + 2 * q;
+      split_pair(k < kvalid ? src[2 * q] : 0.f, k + 1 < kvalid ? src[2 * q + 1] : 0.f, hi[q], lo[q]);
+    }
   }
   out[(size_t)tile * 4096 + u] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   out[(size_t)tile * 4096 + 2048 + u] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -517,9 +520,9 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
 size_t gemm_umma_pack_bytes(int N) { return (size_t)((N + 127) / 128) * GU_TILE_BYTES; }
 
 // Preconditions (checked by the caller): K == 128, N % 4 == 0, x / y 16-byte aligned, no residual.
-int launch_gemm_umma_pack(const float* w, int ldw, int N, void* wpack, cudaStream_t st) {
+int launch_gemm_umma_pack(const float* w, int ldw, int N, void* wpack, cudaStream_t st, int kvalid) {
   const int ntiles = (N + 127) / 128;
-  gemm_umma_pack_kernel<<<(ntiles * 2048 + 255) / 256, 256, 0, st>>>(w, ldw, N, static_cast<uint4*>(wpack));
+  gemm_umma_pack_kernel<<<(ntiles * 2048 + 255) / 256, 256, 0, st>>>(w, ldw, N, static_cast<uint4*>(wpack), kvalid);
   PF_CHECK_LAUNCH();
   return PF_OK;
 }

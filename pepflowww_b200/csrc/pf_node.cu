@@ -11,13 +11,16 @@ namespace pf {
 __global__ void mix_features_kernel(const float* __restrict__ node, const float* __restrict__ emb,
                                     const int64_t* __restrict__ seqs, const float* __restrict__ t,
                                     const float* __restrict__ tfreq, const float* __restrict__ angles,
-                                    const float* __restrict__ afreq, float* __restrict__ x, int B, int L) {
-  const size_t total = (size_t)B * L * NMIX;
+                                    const float* __restrict__ afreq, float* __restrict__ x, int B, int L, int ldx) {
+  // ldx = NMIX, or NMIX rounded up to a multiple of 128 with zero fill (the K loop of the fused layer chain)
+  const size_t total = (size_t)B * L * ldx;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int col = (int)(idx % NMIX);
-    const size_t row = idx / NMIX;
+    const int col = (int)(idx % ldx);
+    const size_t row = idx / ldx;
     float v;
-    if (col < 128) {
+    if (col >= NMIX) {
+      v = 0.f;
+    } else if (col < 128) {
       v = node[row * 128 + col];
     } else if (col < 256) {
       v = emb[seqs[row] * 128 + (col - 128)];
@@ -353,11 +356,11 @@ __global__ void ipa_points_kernel(const float* __restrict__ proj, const float* _
 
 // ---------------------------------------------------------------- launchers (internal)
 int launch_mix_features(const float* node, const float* emb, const int64_t* seqs, const float* t, const float* tfreq,
-                        const float* angles, const float* afreq, float* x, int B, int L, cudaStream_t st) {
-  const size_t total = (size_t)B * L * NMIX;
+                        const float* angles, const float* afreq, float* x, int B, int L, cudaStream_t st, int ldx) {
+  const size_t total = (size_t)B * L * ldx;
   if (total == 0) return PF_OK;
   const int blocks = (int)min((size_t)(num_sms() * 8), (total + 255) / 256);
-  mix_features_kernel<<<blocks, 256, 0, st>>>(node, emb, seqs, t, tfreq, angles, afreq, x, B, L);
+  mix_features_kernel<<<blocks, 256, 0, st>>>(node, emb, seqs, t, tfreq, angles, afreq, x, B, L, ldx);
   PF_CHECK_LAUNCH();
   return PF_OK;
 }
