@@ -72,29 +72,42 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps instead of hanging the device.
+// Blocking wait.  The waiting warp parks in the barrier unit (suspend-time hint) instead of spinning through a counted
+// loop: the spin instructions compete for issue slots with the warps that do the work.  -DPF_BOUNDED_WAIT restores the
+// counted loop that traps on a protocol bug instead of hanging the device (bring-up builds).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef PF_BOUNDED_WAIT
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 28)) __trap();
   }
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "PF_WAITC:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra PF_DONEC;\n\t"
+      "bra PF_WAITC;\n\t"
+      "PF_DONEC:\n\t}\n" ::"r"(bar),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+#endif
 }
 
 // CTA-scope variant for kernels without a cluster: the .cluster acquire above makes ptxas emit CCTL.IVALL (an L1
-// invalidate) after every successful wait
+// invalidate) after every successful wait.  No spin counter and a long suspend-time hint: a waiting warp parks in
+// the barrier unit instead of burning issue slots the other warps of its scheduler need (the bounded spin loop was
+// 12 % of all instructions the IPA kernel executed).
 __device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0, ok = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 28)) __trap();
-  }
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "PF_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra PF_DONE;\n\t"
+      "bra PF_WAIT;\n\t"
+      "PF_DONE:\n\t}\n" ::"r"(bar),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
 }
 
 // plain local arrive / arrive announcing `bytes` of bulk-copy traffic that will complete on this barrier
