@@ -1274,7 +1274,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
       for (int jt = 0; jt < JT; ++jt) {
         const int par = jt & 1;
         if (jt + 1 < JT) next_bias_tile(par ^ 1);
-        mbar_wait_cta(bar_p + 8 * par, (jt >> 1) & 1);       // the head warps have published P / alpha of the tile
+        mbar_wait_cta_relaxed(bar_p + 8 * par, (jt >> 1) & 1);   // the head warps have published P / alpha of the tile
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           opair_row(zgen + oslot * 2048, r, par);

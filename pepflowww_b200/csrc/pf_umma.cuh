@@ -110,6 +110,22 @@ __device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// The same for waits that are off the critical path (a producer-side warp group waiting for its consumers): a failed
+// try_wait additionally sleeps, so the retries of a long wait do not take issue slots either.
+__device__ __forceinline__ void mbar_wait_cta_relaxed(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra PF_DONER;\n\t"
+      "PF_WAITR:\n\t"
+      "nanosleep.u32 96;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@!p bra PF_WAITR;\n\t"
+      "PF_DONER:\n\t}\n" ::"r"(bar),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+
 // plain local arrive / arrive announcing `bytes` of bulk-copy traffic that will complete on this barrier
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
