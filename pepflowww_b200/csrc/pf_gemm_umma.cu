@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(GU_THREADS, 1) gemm_umma_kernel(const __grid_c
         const int n = nt * 128 + rl;
         sbias[buf * 128 + rl] = (a.bias && n < a.N) ? a.bias[n] : 0.f;
       }
-      mbar_wait(bar(GU_BAR_ACCFULL + buf), ph);
+      mbar_wait_cta(bar(GU_BAR_ACCFULL + buf), ph);
       tc_fence_after();
       // the previous tile's TMA stores must have read the staging buffer before it is overwritten
       if (nt > 0) {
@@ -169,13 +169,13 @@ __global__ void __launch_bounds__(GU_THREADS, 1) gemm_umma_kernel(const __grid_c
   } else if (warp == 4) {
     // ================================ MMA issuer ==================================================
     const uint32_t idesc = idesc_f16(128, 128);
-    mbar_wait(bar(GU_BAR_A), 0);
+    mbar_wait_cta(bar(GU_BAR_A), 0);
     tc_fence_after();
     for (int nt = 0; nt < ntiles; ++nt) {
       const int buf = nt & 1;
       const uint32_t ph = (nt >> 1) & 1u;
-      mbar_wait(bar(GU_BAR_WFULL + buf), ph);
-      if (nt >= 2) mbar_wait(bar(GU_BAR_ACCEMPTY + buf), ((nt >> 1) - 1) & 1u);
+      mbar_wait_cta(bar(GU_BAR_WFULL + buf), ph);
+      if (nt >= 2) mbar_wait_cta(bar(GU_BAR_ACCEMPTY + buf), ((nt >> 1) - 1) & 1u);
       tc_fence_after();
       const uint32_t wt = sbase + GU_SM_W + buf * GU_TILE_BYTES;
       const uint32_t d = tmem + GU_COL_ACC + 128 * buf;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(GU_THREADS, 1) gemm_umma_kernel(const __grid_c
     // ================================ W producer ==================================================
     for (int nt = 0; nt < ntiles; ++nt) {
       const int buf = nt & 1;
-      if (nt >= 2) mbar_wait(bar(GU_BAR_WEMPTY + buf), ((nt >> 1) - 1) & 1u);
+      if (nt >= 2) mbar_wait_cta(bar(GU_BAR_WEMPTY + buf), ((nt >> 1) - 1) & 1u);
       mbar_arrive_expect_tx(bar(GU_BAR_WFULL + buf), GU_TILE_BYTES);
       bulk_g2s(sbase + GU_SM_W + buf * GU_TILE_BYTES, a.wpack + (size_t)nt * 4096, GU_TILE_BYTES, bar(GU_BAR_WFULL + buf));
     }
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
     for (int kc = 0; kc < a.kchunks; ++kc) {
       const int abuf = kc & 1;
       if (kc >= 2) {                                          // the MMAs of chunk kc - 2 have read this buffer
-        mbar_wait(bar(GU_BAR_AFREE + abuf), ((kc >> 1) - 1) & 1u);
+        mbar_wait_cta(bar(GU_BAR_AFREE + abuf), ((kc >> 1) - 1) & 1u);
         tc_fence_after();
       }
       const float4* xp = reinterpret_cast<const float4*>(a.x + ((size_t)(live ? m : 0) * a.kchunks + kc) * 128);
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
           const int n = nt * 128 + rl;
           sbias[buf * 128 + rl] = (st.bias && n < st.N) ? st.bias[n] : 0.f;
         }
-        mbar_wait(bar(GU_BAR_ACCFULL + buf), ph);
+        mbar_wait_cta(bar(GU_BAR_ACCFULL + buf), ph);
         tc_fence_after();
         // earlier TMA stores must have read the staging buffer before it is overwritten
         if (stores_pending && tid == 0) bulk_wait_read0();
@@ -457,23 +457,23 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
       const int ntiles = (a.st[s].N + 127) / 128;
       const int kchunks = s == 0 ? a.kchunks : 1;
       if (a_new && kchunks == 1) {                            // the A operand was (re)written by the row threads
-        mbar_wait(bar(GU_BAR_A), a_ph);
+        mbar_wait_cta(bar(GU_BAR_A), a_ph);
         a_ph ^= 1u;
         tc_fence_after();
       }
       a_new = (a.st[s].flags & CH_NEXT_A) != 0;
       for (int nt = 0; nt < ntiles; ++nt, ++ai) {
         const int abuf_acc = ai & 1;
-        if (ai >= 2) mbar_wait(bar(GU_BAR_ACCEMPTY + abuf_acc), ((ai >> 1) - 1) & 1u);
+        if (ai >= 2) mbar_wait_cta(bar(GU_BAR_ACCEMPTY + abuf_acc), ((ai >> 1) - 1) & 1u);
         const uint32_t d = tmem + GU_COL_ACC + 128 * abuf_acc;
         for (int kc = 0; kc < kchunks; ++kc, ++wi) {
           const int buf = wi & 1;
           uint32_t acol = GU_COL_A;
           if (kchunks > 1) {                                  // K loop: chunk kc sits in A buffer kc & 1
-            mbar_wait(bar((kc & 1) ? GU_BAR_A1 : GU_BAR_A), (kc >> 1) & 1u);
+            mbar_wait_cta(bar((kc & 1) ? GU_BAR_A1 : GU_BAR_A), (kc >> 1) & 1u);
             if (kc & 1) acol = CH_COL_RES;
           }
-          mbar_wait(bar(GU_BAR_WFULL + buf), (wi >> 1) & 1u);
+          mbar_wait_cta(bar(GU_BAR_WFULL + buf), (wi >> 1) & 1u);
           tc_fence_after();
           const uint32_t wt = sbase + GU_SM_W + buf * GU_TILE_BYTES;
 #pragma unroll
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
       const int ntiles = ((a.st[s].N + 127) / 128) * (s == 0 ? a.kchunks : 1);   // K loop: one tile per chunk
       for (int nt = 0; nt < ntiles; ++nt, ++it) {
         const int buf = it & 1;
-        if (it >= 2) mbar_wait(bar(GU_BAR_WEMPTY + buf), ((it >> 1) - 1) & 1u);
+        if (it >= 2) mbar_wait_cta(bar(GU_BAR_WEMPTY + buf), ((it >> 1) - 1) & 1u);
         mbar_arrive_expect_tx(bar(GU_BAR_WFULL + buf), GU_TILE_BYTES);
         bulk_g2s(sbase + GU_SM_W + buf * GU_TILE_BYTES, a.st[s].wpack + (size_t)nt * 4096, GU_TILE_BYTES,
                  bar(GU_BAR_WFULL + buf));
