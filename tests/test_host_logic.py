@@ -82,3 +82,40 @@ def test_time_frequencies_bitwise():
     from pepflowww_b200.utils_time import get_time_embedding
     t = torch.tensor([0.01, 0.5, 1.0])
     assert torch.equal(get_time_embedding(t, 128, 2056), orc.time_embedding(t))
+
+
+def test_embedder_kernel_constants_match_the_concatenated_first_layers():
+    """The fused embedder kernels take the embedding lookups already pushed through the first Linear of their MLPs
+    (EdgeEmbedder._kernel_constants / NodeEmbedder._kernel_constants).  On CPU: the table form equals the reference's
+    concatenate-then-Linear form (models_con/edge.py:104-105, models_con/node.py:98-99)."""
+    import torch
+
+    from pepflowww_b200.edge import EdgeEmbedder
+    from pepflowww_b200.node import NodeEmbedder
+    torch.manual_seed(0)
+    ee = EdgeEmbedder(64, 15)
+    torch.nn.init.normal_(ee.aapair_to_distcoef.weight, std=0.02)
+    c = ee._kernel_constants()
+    assert [tuple(t.shape) for t in c] == [(484, 225), (484, 64), (65, 64), (225, 64), (64,), (64, 64), (64,), (64, 64),
+                                           (26, 64), (64,), (64, 64), (64,), (64, 64), (64,)]
+    n = 50
+    aa_pair, rel = torch.randint(0, 484, (n,)), torch.randint(0, 65, (n,))
+    same = torch.randint(0, 2, (n, 1)).float()
+    f_d, f_h = torch.rand(n, 64), torch.randn(n, 26)
+    ref = ee.out_mlp[0](torch.cat([ee.aa_pair_embed(aa_pair), ee.relpos_embed(rel) * same, f_d, f_h], dim=-1))
+    got = c[1][aa_pair] + same * c[2][rel] + f_d @ c[7] + f_h @ c[8] + c[9]
+    assert torch.allclose(got, ref, atol=1e-5)
+    assert torch.allclose(c[0], torch.nn.functional.softplus(ee.aapair_to_distcoef.weight))
+
+    ne = NodeEmbedder(128, 15)
+    c = ne._kernel_constants()
+    assert [tuple(t.shape) for t in c] == [(22, 256), (990, 256), (39, 256), (256, 128), (128,), (128, 128), (128,),
+                                           (128, 128), (128,)]
+    aa = torch.randint(0, 22, (n,))
+    crd, dih = torch.randn(n, 45), torch.randn(n, 39)
+    place = torch.zeros(n, 22, 45)
+    place[torch.arange(n), aa] = crd
+    ref = ne.mlp[0](torch.cat([ne.aatype_embed(aa), place.reshape(n, 990), dih], dim=-1))
+    w1c = c[1].reshape(22, 45, 256)
+    got = c[0][aa] + torch.einsum("nk,nkc->nc", crd, w1c[aa]) + dih @ c[2]
+    assert torch.allclose(got, ref, atol=1e-5)
