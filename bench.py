@@ -172,7 +172,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"],
             "unit": "peptides/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg4: {args.batch} complexes/GPU x {args.gpus} GPU, {args.pocket}-res pocket / "
+            "config": {"workload": f"{cfg_name(args)}: {args.batch} complexes/GPU x {args.gpus} GPU, {args.pocket}-res pocket / "
                                    f"{args.peptide}-res peptide (L={args.pocket + args.peptide}), {EULER_STEPS} Euler steps",
                        "step": f"bounded CPU sample: Euler iterations over {args.cpu_batch} complexes of the same shape on "
                                f"the host cores, extrapolated per complex"},
@@ -180,6 +180,15 @@ def run_reference(args):
             "e2e": {"value": cb["value"], "unit": "peptides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cfg_name(args):
+    """BASELINE.json config the shape corresponds to (cfg4 = the headline 256 + 15 residue shard, cfg2 = 128 + 12)."""
+    if (args.pocket, args.peptide) == (256, 15):
+        return "cfg4"
+    if (args.pocket, args.peptide) == (128, 12):
+        return "cfg2"
+    return "custom"
 
 
 def ncu_traffic(kernel, impl, B, L):
@@ -327,7 +336,7 @@ def run_ours(args):
         line = {"metric": METRIC,
                 "value": value, "unit": "peptides/s", "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"cfg4: {B} complexes/GPU x {n_gpus} GPU, {args.pocket}-res pocket / "
+                "config": {"workload": f"{cfg_name(args)}: {B} complexes/GPU x {n_gpus} GPU, {args.pocket}-res pocket / "
                                        f"{args.peptide}-res peptide (L={L}), {EULER_STEPS} Euler steps",
                            "step": "one Euler iteration (GAEncoder.forward + post-processing + manifold update) over "
                                    "the per-GPU batch; value = complexes / (200 x step time)",
