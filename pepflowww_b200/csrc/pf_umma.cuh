@@ -118,7 +118,7 @@ __device__ __forceinline__ void mbar_wait_cta_relaxed(uint32_t bar, uint32_t par
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra PF_DONER;\n\t"
       "PF_WAITR:\n\t"
-      "nanosleep.u32 96;\n\t"
+      "nanosleep.u32 320;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@!p bra PF_WAITR;\n\t"
       "PF_DONER:\n\t}\n" ::"r"(bar),
