@@ -239,6 +239,28 @@ int pf_node_embed(const int64_t* aa, const int64_t* res_nb, const int64_t* chain
                   const float* w1d_t, const float* w2_t, const float* b2, const float* w3_t, const float* b3,
                   const float* w4_t, const float* b4, float* out, int N, int L, int atoms_in, void* stream);
 
+/* ---- post-sampling reconstruction ----------------------------------------------
+ * full_atom_reconstruction, models_con/torsion.py:140-226 (with get_heavyatom_mask :126-138 as an optional second
+ * output): backbone frames rot[n,3,3] / trans[n,3], torsions angles[n,5] = (psi, chi1..chi4) in radians and residue
+ * types aa[n] i64 -> pos14[n,14,3]; optionally (NULL to skip) R_ret[n,6,3,3] / t_ret[n,6,3] = the backbone, psi and
+ * chi1..chi4 frames, and mask_out[n,15] u8 = heavyatom_mask_table[aa] (table [22,15] u8, torsion.py:122-124).
+ * Constant tables (pepflow/modules/protein/constants.py:665-749): rigid_rot[21,8,3,3], rigid_trans[21,8,3],
+ * atom_group[21,14] i32, atom_pos[21,14,3].  The reference indexes its 21-row tables with aa and raises on
+ * aa > 20; here such rows (PAD) get zero rigid groups - every atom lands on the backbone origin and the mask is 0 -
+ * and the Python wrapper raises IndexError like the reference.                                                  */
+int pf_full_atom_reconstruction(const float* rot, const float* trans, const float* angles, const int64_t* aa,
+                                const float* rigid_rot, const float* rigid_trans, const int32_t* atom_group,
+                                const float* atom_pos, const uint8_t* heavyatom_mask_table, float* pos14,
+                                float* R_ret, float* t_ret, uint8_t* mask_out, long long n, void* stream);
+
+/* reconstruct_backbone, pepflow/modules/common/geometry.py:446-489: rot[N,L,3,3], trans[N,L,3], aa / chain_nb /
+ * res_nb [N,L] i64, mask[N,L] u8 -> pos_bb[N,L,4,3] = N, CA, C, O.  psi of residue i is measured on the rebuilt
+ * backbone (N_i, CA_i, C_i, N_{i+1}) and is 0 at chain ends / gaps / masked residues (:355-390).  Tables
+ * bb_coords[21,3,3], bb_oxygen[21,3] (constants.py:878-890); aa is clamped to [0, 20] (:462).                   */
+int pf_reconstruct_backbone(const float* rot, const float* trans, const int64_t* aa, const int64_t* chain_nb,
+                            const int64_t* res_nb, const uint8_t* mask, const float* bb_coords,
+                            const float* bb_oxygen, float* pos_bb, int N, int L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

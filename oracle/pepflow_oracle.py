@@ -534,3 +534,59 @@ def zero_center_part(pos, gen_mask, res_mask):
     g = gen_mask.float()
     center = (pos * g[..., None]).sum(1) / (g.sum(-1, keepdim=True) + 1e-8)
     return (pos - center[:, None]) * res_mask.float()[..., None], center[:, None]
+
+
+# ----------------------------------------------------------------------------- post-sampling reconstruction
+# SURVEY.md section 8f rank 3.  `tables` = the dict of pepflowww_b200/data/restype_rigid_tables.npz as CPU tensors
+# (rigid_rot [21,8,3,3], rigid_trans [21,8,3], atom_group [21,14], atom_pos [21,14,3], bb_coords [21,3,3],
+# bb_oxygen [21,3]) - the reference's pepflow/modules/protein/constants.py:665-668,878-879.
+
+
+def _rot_x(angle):
+    """[[1,0,0],[0,c,-s],[0,s,c]] per angle (models_con/torsion.py:68-96, geometry.py:471-479)."""
+    s, c = torch.sin(angle), torch.cos(angle)
+    R = torch.zeros(angle.shape + (3, 3), dtype=angle.dtype)
+    R[..., 0, 0] = 1.0
+    R[..., 1, 1] = c
+    R[..., 1, 2] = -s
+    R[..., 2, 1] = s
+    R[..., 2, 2] = c
+    return R
+
+
+def _compose(R1, t1, R2, t2):
+    """(R1, t1) o (R2, t2) (pepflow/modules/common/geometry.py:175-180)."""
+    return R1 @ R2, (R1 @ t2[..., None])[..., 0] + t1
+
+
+def full_atom_reconstruction(tables, R_bb, t_bb, angles, aa):
+    """models_con/torsion.py:140-226: (pos14 [B,L,14,3], R [B,L,6,3,3], t [B,L,6,3]); compose_chain folds from the
+    right (geometry.py:183-189), so each torsion frame is parent o (group o Rx)."""
+    rr, rt = tables["rigid_rot"][aa], tables["rigid_trans"][aa]         # [B,L,8,3,3], [B,L,8,3]
+    zero = torch.zeros_like(t_bb)
+    frames = [(R_bb, t_bb)]
+    for f in range(1, 6):                                                # psi, chi1..chi4 = rigid groups 3..7
+        parent = frames[0] if f <= 2 else frames[f - 1]
+        inner = _compose(rr[:, :, f + 2], rt[:, :, f + 2], _rot_x(angles[:, :, f - 1]), zero)
+        frames.append(_compose(parent[0], parent[1], inner[0], inner[1]))
+    group = tables["atom_group"][aa].long()                              # [B,L,14]
+    fidx = torch.where(group < 3, torch.zeros_like(group), group - 2)
+    R_all = torch.stack([f[0] for f in frames], dim=2)
+    t_all = torch.stack([f[1] for f in frames], dim=2)
+    R_atom = torch.gather(R_all, 2, fidx[..., None, None].expand(-1, -1, -1, 3, 3))
+    t_atom = torch.gather(t_all, 2, fidx[..., None].expand(-1, -1, -1, 3))
+    pos14 = (R_atom @ tables["atom_pos"][aa][..., None])[..., 0] + t_atom
+    return pos14, R_all, t_all
+
+
+def reconstruct_backbone(tables, R, t, aa, chain_nb, res_nb, mask):
+    """pepflow/modules/common/geometry.py:446-489: N, CA, C from the backbone frame, O from the psi frame with psi
+    measured on the rebuilt backbone (:355-390; terminus flags pepflow/modules/common/topology.py:5-24)."""
+    aa = aa.clamp(0, 20)
+    bb = (R[:, :, None] @ tables["bb_coords"][aa][..., None])[..., 0] + t[:, :, None]     # [B,L,3,3]
+    consec = ((res_nb[:, 1:] - res_nb[:, :-1]).abs() == 1) & (chain_nb[:, 1:] == chain_nb[:, :-1]) & mask[:, :-1].bool()
+    psi = dihedral(bb[:, :-1, 0], bb[:, :-1, 1], bb[:, :-1, 2], bb[:, 1:, 0]) * consec
+    psi = torch.cat([psi, torch.zeros_like(psi[:, :1])], dim=1)
+    R_psi, t_psi = _compose(R, t, _rot_x(psi), torch.zeros_like(t))
+    O = (R_psi @ tables["bb_oxygen"][aa][..., None])[..., 0] + t_psi
+    return torch.cat([bb, O[:, :, None]], dim=2)

@@ -56,6 +56,8 @@ SIGNATURES = {
     "pf_ga_encoder_forward": (_i, [_p] * 15 + [_sz] + [_i] * 2 + [_p]),
     "pf_edge_embed": (_i, [_p] * 21 + [_i] * 3 + [_p]),
     "pf_node_embed": (_i, [_p] * 16 + [_i] * 3 + [_p]),
+    "pf_full_atom_reconstruction": (_i, [_p] * 13 + [C.c_longlong, _p]),
+    "pf_reconstruct_backbone": (_i, [_p] * 9 + [_i] * 2 + [_p]),
 }
 
 # enum sizes of include/pepflow_b200.h

@@ -77,3 +77,25 @@ def _build_torsions_mask():
 
 restype_to_heavyatom_masks = _build_heavyatom_masks()
 torsions_mask = _build_torsions_mask()
+
+
+# ---- rigid-group tables of the post-sampling reconstruction (reference constants.py:665-749, 878-890) ----------
+# Ideal-geometry data, shipped as pepflowww_b200/data/restype_rigid_tables.npz (scripts/make_restype_tables.py).
+_RIGID_TABLES = {}
+
+
+def rigid_tables(device="cpu"):
+    """dict of tensors on `device`: rigid_rot [21,8,3,3], rigid_trans [21,8,3], atom_group [21,14] i32,
+    atom_pos [21,14,3], bb_coords [21,3,3], bb_oxygen [21,3], heavyatom_mask [22,15] u8."""
+    import os
+
+    import numpy as np
+    device = torch.device(device)
+    key = (device.type, device.index)
+    if key not in _RIGID_TABLES:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "restype_rigid_tables.npz")
+        with np.load(path) as z:
+            t = {k: torch.from_numpy(z[k]).to(device).contiguous() for k in z.files}
+        t["heavyatom_mask"] = restype_to_heavyatom_masks.to(torch.uint8).to(device).contiguous()
+        _RIGID_TABLES[key] = t
+    return _RIGID_TABLES[key]

@@ -18,6 +18,7 @@
 // the per-row tables (softplus coefficients and T_aa rows of aa_i) are re-staged per row; a thread owns one pair and
 // keeps its activations in registers; the output tile is staged in shared memory and written as full 128-byte lines.
 #include "pf_common.cuh"
+#include "pf_geom.cuh"
 
 namespace pf {
 
@@ -68,22 +69,6 @@ __device__ __forceinline__ void ee_axpy64(float (&y)[EE_F], float x, const float
     y[n] = fmaf(x, v.x, y[n]); y[n + 1] = fmaf(x, v.y, y[n + 1]);
     y[n + 2] = fmaf(x, v.z, y[n + 2]); y[n + 3] = fmaf(x, v.w, y[n + 3]);
   }
-}
-
-// geometry.py:296-313: signed dihedral of four points, NaN (degenerate geometry, e.g. padded residues) -> 0
-__device__ __forceinline__ float ee_dihedral(const float* p0, const float* p1, const float* p2, const float* p3) {
-  const float v0x = p2[0] - p1[0], v0y = p2[1] - p1[1], v0z = p2[2] - p1[2];
-  const float v1x = p0[0] - p1[0], v1y = p0[1] - p1[1], v1z = p0[2] - p1[2];
-  const float v2x = p3[0] - p2[0], v2y = p3[1] - p2[1], v2z = p3[2] - p2[2];
-  const float u1x = v0y * v1z - v0z * v1y, u1y = v0z * v1x - v0x * v1z, u1z = v0x * v1y - v0y * v1x;
-  const float u2x = v0y * v2z - v0z * v2y, u2y = v0z * v2x - v0x * v2z, u2z = v0x * v2y - v0y * v2x;
-  const float l1 = sqrtf(u1x * u1x + u1y * u1y + u1z * u1z), l2 = sqrtf(u2x * u2x + u2y * u2y + u2z * u2z);
-  const float d = (u1x / l1) * (u2x / l2) + (u1y / l1) * (u2y / l2) + (u1z / l1) * (u2z / l2);
-  if (!(d == d)) return 0.f;                       // nan_to_num
-  const float cx = v1y * v2z - v1z * v2y, cy = v1z * v2x - v1x * v2z, cz = v1x * v2y - v1y * v2x;
-  const float s = cx * v0x + cy * v0y + cz * v0z;
-  const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
-  return sg * acosf(fminf(fmaxf(d, -0.999999f), 0.999999f));
 }
 
 __global__ void __launch_bounds__(EE_MAXT, 1) edge_embed_kernel(EdgeEmbedArgs a) {
@@ -176,7 +161,7 @@ __global__ void __launch_bounds__(EE_MAXT, 1) edge_embed_kernel(EdgeEmbedArgs a)
         for (int k = 0; k < EE_F; ++k) ee_axpy64(h, fmaxf(y[k], 0.f) * psm, sm + EE_OFF_WO1D + k * EE_F);
         {
           // phi = dihedral(C_i, N_j, CA_j, C_j), psi = dihedral(N_i, CA_i, C_i, N_j); atoms N 0, CA 1, C 2
-          const float ang[2] = {ee_dihedral(s_pi + 6, pj, pj + 3, pj + 6), ee_dihedral(s_pi, s_pi + 3, s_pi + 6, pj)};
+          const float ang[2] = {dihedral4(s_pi + 6, pj, pj + 3, pj + 6), dihedral4(s_pi, s_pi + 3, s_pi + 6, pj)};
           const float fr[6] = {1.f, 2.f, 3.f, 1.f, 1.f / 2.f, 1.f / 3.f};
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
@@ -326,14 +311,14 @@ __global__ void __launch_bounds__(NE_T) node_embed_kernel(NodeEmbedArgs a) {
           const int64_t dr = rn - a.res_nb[row - 1];
           on = (dr == 1 || dr == -1) && cn == a.chain_nb[row - 1] && a.mask[(size_t)(row - 1) * a.A_in + 1] != 0;
           const float* Q = P - (size_t)a.A_in * 3;               // residue j - 1
-          ang = which == 0 ? ee_dihedral(Q + 3, Q + 6, P, P + 3) : ee_dihedral(Q + 6, P, P + 3, P + 6);
+          ang = which == 0 ? dihedral4(Q + 3, Q + 6, P, P + 3) : dihedral4(Q + 6, P, P + 3, P + 6);
         }
       } else {
         on = j < L - 1;
         if (on) {
           const int64_t dr = a.res_nb[row + 1] - rn;
           on = (dr == 1 || dr == -1) && cn == a.chain_nb[row + 1] && mk[1] != 0;
-          ang = ee_dihedral(P, P + 3, P + 6, P + (size_t)a.A_in * 3);
+          ang = dihedral4(P, P + 3, P + 6, P + (size_t)a.A_in * 3);
         }
       }
       // structure mask of the residue and both neighbours, with torch.roll's wrap-around (node.py:90-96)

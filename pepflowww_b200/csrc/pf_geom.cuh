@@ -1,0 +1,37 @@
+// Small geometry device functions shared by the once-per-sample kernels (pf_embed.cu, pf_recon.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pf {
+
+// geometry.py:296-313: signed dihedral of four points, NaN (degenerate geometry, e.g. padded residues) -> 0
+__device__ __forceinline__ float dihedral4(const float* p0, const float* p1, const float* p2, const float* p3) {
+  const float v0x = p2[0] - p1[0], v0y = p2[1] - p1[1], v0z = p2[2] - p1[2];
+  const float v1x = p0[0] - p1[0], v1y = p0[1] - p1[1], v1z = p0[2] - p1[2];
+  const float v2x = p3[0] - p2[0], v2y = p3[1] - p2[1], v2z = p3[2] - p2[2];
+  const float u1x = v0y * v1z - v0z * v1y, u1y = v0z * v1x - v0x * v1z, u1z = v0x * v1y - v0y * v1x;
+  const float u2x = v0y * v2z - v0z * v2y, u2y = v0z * v2x - v0x * v2z, u2z = v0x * v2y - v0y * v2x;
+  const float l1 = sqrtf(u1x * u1x + u1y * u1y + u1z * u1z), l2 = sqrtf(u2x * u2x + u2y * u2y + u2z * u2z);
+  const float d = (u1x / l1) * (u2x / l2) + (u1y / l1) * (u2y / l2) + (u1z / l1) * (u2z / l2);
+  if (!(d == d)) return 0.f;                       // nan_to_num
+  const float cx = v1y * v2z - v1z * v2y, cy = v1z * v2x - v1x * v2z, cz = v1x * v2y - v1y * v2x;
+  const float s = cx * v0x + cy * v0y + cz * v0z;
+  const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+  return sg * acosf(fminf(fmaxf(d, -0.999999f), 0.999999f));
+}
+
+// C = A B for row-major 3x3 matrices
+__device__ __forceinline__ void mat3_mul(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      C[i * 3 + j] = fmaf(A[i * 3 + 2], B[6 + j], fmaf(A[i * 3 + 1], B[3 + j], A[i * 3] * B[j]));
+}
+// y = R x + t
+__device__ __forceinline__ void rigid_apply(const float* R, const float* t, const float* x, float* y) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) y[i] = fmaf(R[i * 3 + 2], x[2], fmaf(R[i * 3 + 1], x[1], R[i * 3] * x[0])) + t[i];
+}
+
+}  // namespace pf

@@ -64,3 +64,12 @@ def pairwise_dihedrals(pos_atoms):
     phi = dihedral_from_four_points(rows(pC), cols(pN), cols(pCA), cols(pC))
     psi = dihedral_from_four_points(rows(pN), rows(pCA), rows(pC), cols(pN))
     return torch.stack([phi, psi], dim=-1)
+
+
+def reconstruct_backbone(R, t, aa, chain_nb, res_nb, mask):
+    """N, CA, C, O [N, L, 4, 3] from backbone frames and residue types (reference geometry.py:446-489; the step after
+    FlowModel.sample in models_con/sample.py:46,77).  One kernel (pf_reconstruct_backbone); CUDA tensors only."""
+    from . import constants, ops
+    if not R.is_cuda:
+        raise RuntimeError("reconstruct_backbone: CUDA tensors required (no CPU fallback)")
+    return ops.reconstruct_backbone(R, t, aa, chain_nb, res_nb, mask, constants.rigid_tables(R.device))

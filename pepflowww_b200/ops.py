@@ -250,3 +250,35 @@ def node_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, cons
                             ptr(m, U8), ptr(sm, U8, allow_none=True), *[ptr(c) for c in cs], ptr(out), N, L,
                             pos.shape[2], stream()))
     return out
+
+
+def full_atom_reconstruction(rot, trans, angles, aa, tables, want_frames=True, want_mask=False):
+    """full_atom_reconstruction (models_con/torsion.py:140-226) as one kernel (pf_full_atom_reconstruction).
+    `tables` = constants.rigid_tables(device).  Returns (pos14 [B,L,14,3], R [B,L,6,3,3] | None, t [B,L,6,3] | None,
+    mask [B,L,15] bool | None)."""
+    lib = _lib.lib_for(rot.device)
+    B, L = aa.shape
+    n = B * L
+    dev = rot.device
+    pos14 = torch.empty(B, L, 14, 3, device=dev, dtype=F32)
+    R_ret = torch.empty(B, L, 6, 3, 3, device=dev, dtype=F32) if want_frames else None
+    t_ret = torch.empty(B, L, 6, 3, device=dev, dtype=F32) if want_frames else None
+    mask = torch.empty(B, L, 15, device=dev, dtype=U8) if want_mask else None
+    check(lib.pf_full_atom_reconstruction(
+        ptr(_c(rot)), ptr(_c(trans)), ptr(_c(angles)), ptr(_c(aa, I64), I64), ptr(tables["rigid_rot"]),
+        ptr(tables["rigid_trans"]), ptr(tables["atom_group"], torch.int32), ptr(tables["atom_pos"]),
+        ptr(tables["heavyatom_mask"], U8), ptr(pos14), ptr(R_ret, allow_none=True), ptr(t_ret, allow_none=True),
+        ptr(mask, U8, allow_none=True), n, stream()))
+    return pos14, R_ret, t_ret, (mask.view(torch.bool) if want_mask else None)
+
+
+def reconstruct_backbone(rot, trans, aa, chain_nb, res_nb, mask, tables):
+    """reconstruct_backbone (pepflow/modules/common/geometry.py:446-489) as one kernel: [B,L,4,3] = N, CA, C, O."""
+    lib = _lib.lib_for(rot.device)
+    B, L = aa.shape
+    out = torch.empty(B, L, 4, 3, device=rot.device, dtype=F32)
+    m = _c(mask, torch.bool).view(U8)
+    check(lib.pf_reconstruct_backbone(ptr(_c(rot)), ptr(_c(trans)), ptr(_c(aa, I64), I64), ptr(_c(chain_nb, I64), I64),
+                                      ptr(_c(res_nb, I64), I64), ptr(m, U8), ptr(tables["bb_coords"]),
+                                      ptr(tables["bb_oxygen"]), ptr(out), B, L, stream()))
+    return out

@@ -119,3 +119,36 @@ def test_embedder_kernel_constants_match_the_concatenated_first_layers():
     w1c = c[1].reshape(22, 45, 256)
     got = c[0][aa] + torch.einsum("nk,nkc->nc", crd, w1c[aa]) + dih @ c[2]
     assert torch.allclose(got, ref, atol=1e-5)
+
+
+def test_heavyatom_mask_and_pdb_writer_round_trip():
+    """get_heavyatom_mask equals the reference's table gather (golden), and save_pdb's fixed-column records parse back
+    to the atoms that went in (names per residue type, chain split, serial numbers, coordinates to 1e-3)."""
+    from pepflowww_b200 import torsion, writers
+    from pepflowww_b200.constants import AA, heavyatom_names
+    from tests.conftest import load_golden
+    g = load_golden("reconstruction")
+    mask = torsion.get_heavyatom_mask(g["aa"])
+    assert mask.dtype == torch.bool and (mask == g["mask15"]).all()
+    i = 0
+    L = g["aa"].shape[1]
+    data = dict(chain_nb=g["chain_nb"][i], aa=g["aa"][i], resseq=g["res_nb"][i], icode=[" "] * L,
+                chain_id=["A" if c == 0 else "B" for c in g["chain_nb"][i].tolist()],
+                pos_heavyatom=torch.nn.functional.pad(g["pos14"][i], (0, 0, 0, 1)), mask_heavyatom=mask[i])
+    text = writers.save_pdb(data)
+    lines = text.splitlines()
+    assert all(len(ln) == 80 for ln in lines[:-1]) and lines[-1] == "END   "
+    assert sum(ln.startswith("TER") for ln in lines) == 2
+    atoms = writers.parse_pdb_atoms(text)
+    assert len(atoms) == int(mask[i].sum())
+    k = 0
+    for r in range(L):
+        for a, name in enumerate(heavyatom_names(AA(int(g["aa"][i, r])))):
+            if name == "" or not mask[i, r, a]:
+                continue
+            serial, nm, resname, chain, resseq, xyz = atoms[k]
+            assert nm == name and resname == AA(int(g["aa"][i, r])).name and resseq == int(g["res_nb"][i, r])
+            assert chain == ("A" if g["chain_nb"][i, r] == 0 else "B")
+            assert max(abs(x - float(y)) for x, y in zip(xyz, g["pos14"][i, r, a])) < 6e-4
+            k += 1
+    assert [a[0] for a in atoms[:5]] == [1, 2, 3, 4, 5]
