@@ -590,3 +590,47 @@ def reconstruct_backbone(tables, R, t, aa, chain_nb, res_nb, mask):
     R_psi, t_psi = _compose(R, t, _rot_x(psi), torch.zeros_like(t))
     O = (R_psi @ tables["bb_oxygen"][aa][..., None])[..., 0] + t_psi
     return torch.cat([bb, O[:, :, None]], dim=2)
+
+
+# ----------------------------------------------------------------------------- training-loss arithmetic
+# SURVEY.md section 8f rank 4.
+
+
+def flow_losses(sd, batch, noise, torsions_mask, cfg_min_clip=0.9, sigma=1.0, K=20, k=5.0):
+    """FlowModel.forward, models_con/flow_model.py:111-227, with the corruption injected instead of drawn:
+    noise = dict(t [B,1] (already in [min_t, 1 - min_t]), trans_0 [B,L,3] raw normal, rotmats_0, angles_0,
+    seqs_0_simplex (already scaled by k), u_t, u_pred [B,L] uniforms of the two categorical draws)."""
+    enc = encode(sd, batch)
+    gen = batch["generate_mask"]
+    gm, rm = gen.float(), batch["res_mask"].float()
+    R1, x1, a1, s1 = enc["rotmats_1"], enc["trans_1"], enc["angles_1"], enc["seqs_1"]
+    t = noise["t"]
+    x0c, _ = zero_center_part(noise["trans_0"] * sigma, gen, batch["res_mask"])                      # :129-130
+    x_t = torch.where(gen[..., None], (1 - t[..., None]) * x0c + t[..., None] * x1, x1)              # :131-132
+    R_t = torch.where(gen[..., None, None], geodesic_t(t[..., None], R1, noise["rotmats_0"]), R1)    # :134-136
+    a_t = torch.where(gen[..., None], tor_geodesic_t(t[..., None], a1, noise["angles_0"]), a1)       # :138-140
+    sx1 = seq_to_simplex(s1, K, k)
+    sx_t = torch.where(gen[..., None], (1 - t[..., None]) * noise["seqs_0_simplex"] + t[..., None] * sx1, sx1)
+    s_t = torch.where(gen, categorical_from_uniform(torch.softmax(sx_t, -1), noise["u_t"]), s1)     # :147-152
+    pR, px, pa, logits = ga_encoder_forward(sd, t, R_t, x_t, a_t, s_t, enc["node_embed"], enc["edge_embed"],
+                                            gen.long(), batch["res_mask"].long())                   # :159
+    ps = categorical_from_uniform(torch.softmax(logits, -1), noise["u_pred"])
+    ps = torch.where(gen, ps, s1.clamp(0, 19))                                                       # :160-161
+    scale = 1 / (1 - torch.clamp(t[..., None], max=cfg_min_clip))                                    # :165
+    gsum = gm.sum(-1) + 1e-8
+    per = lambda x: (x / gsum).mean()
+    trans_loss = per(((px - x1) ** 2 * gm[..., None]).sum((-1, -2)))                                 # :168-169
+    rot_loss = per((((calc_rot_vf(R_t, R1) - calc_rot_vf(R_t, pR)) * scale) ** 2 * gm[..., None]).sum((-1, -2)))
+    ideal = torch.tensor([[-0.525, 1.363, 0.0], [0.0, 0.0, 0.0], [1.526, 0.0, 0.0]])               # N, CA, C (:178-179)
+    bb = lambda R, x: torch.einsum("blij,aj->blai", R, ideal) + x[:, :, None]
+    bb_loss = per(((bb(R1, x1) - bb(pR, px)) ** 2 * gm[..., None, None]).sum((-1, -2, -3)))          # :183-187
+    ce = torch.nn.functional.cross_entropy(logits.reshape(-1, K), s1.clamp(0, 19).reshape(-1), reduction="none")
+    seqs_loss = per((ce.view(logits.shape[:-1]) * gm).sum(-1))                                       # :191-193
+    aml = torsions_mask[ps]
+    aml = torch.cat([aml, aml], -1).bool() & gen[..., None]                                          # :199-202
+    asum = aml.sum((-1, -2)) + 1e-8
+    vec = lambda x: torch.cat([torch.sin(x), torch.cos(x)], -1)
+    angle_loss = ((((vec(tor_logmap(a_t, a1)) - vec(tor_logmap(a_t, pa))) * scale) ** 2 * aml).sum((-1, -2)) / asum).mean()
+    torsion_loss = (((vec(pa) - vec(a1)) ** 2 * aml).sum((-1, -2)) / asum).mean()                    # :213-218
+    return {"trans_loss": trans_loss, "rot_loss": rot_loss, "bb_atom_loss": bb_loss, "seqs_loss": seqs_loss,
+            "angle_loss": angle_loss, "torsion_loss": torsion_loss}

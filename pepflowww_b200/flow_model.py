@@ -335,13 +335,28 @@ class EulerSampler:
 
 
 def _rot_vf_autograd(mat_t, mat_1):
-    """Differentiable Log(mat_t^T mat_1) for the training loss (generic branch of data/so3_utils.py:167-254;
-    the theta~0 / theta~pi branches carry no useful gradient in the reference either)."""
+    """Differentiable Log(mat_t^T mat_1) for the training loss: the three-branch logarithm of data/so3_utils.py:167-254
+    (theta ~ 0 Taylor, generic theta / (2 sin theta), theta ~ pi from (I + R) / 2 with the reference's sign choice) in
+    torch ops, so the loss value equals the reference's.  The branch masks are piecewise constant; the square root of
+    the theta ~ pi branch is clamped away from 0, where the reference's own backward produces the NaN gradients that
+    train_ddp.py:139-142 zeroes."""
     rel = torch.einsum("...ji,...jk->...ik", mat_t, mat_1)
     v = torch.stack([rel[..., 2, 1] - rel[..., 1, 2], rel[..., 0, 2] - rel[..., 2, 0], rel[..., 1, 0] - rel[..., 0, 1]], dim=-1)
     sin_t = torch.linalg.norm(v, dim=-1) / 2.0
     cos_t = (rel[..., 0, 0] + rel[..., 1, 1] + rel[..., 2, 2] - 1.0) / 2.0
     th = torch.atan2(sin_t, cos_t)
-    safe = sin_t.abs() > 1e-6
-    pref = torch.where(safe, th / (2.0 * torch.where(safe, sin_t, torch.ones_like(sin_t))), torch.full_like(th, 0.5))
-    return v * pref[..., None]
+    near_0 = torch.isclose(th, torch.zeros_like(th))
+    near_pi = torch.isclose(th, torch.full_like(th, math.pi), atol=1e-2) & ~near_0
+    generic = ~(near_0 | near_pi)
+    one = torch.ones_like(th)
+    pref = torch.where(generic, th / (2.0 * torch.where(generic, sin_t, one)), torch.zeros_like(th))
+    pref = torch.where(near_0, 0.5 / (1.0 - th.detach() ** 2 / 6.0), pref)
+    out = v * pref[..., None]
+    if bool(near_pi.any()):
+        diag = torch.diagonal(rel, dim1=-2, dim2=-1)
+        M = (torch.eye(3, device=rel.device, dtype=rel.dtype) + rel) / 2.0
+        axis = torch.sqrt(torch.clamp((1.0 + diag) / 2.0, min=1e-12))
+        row = torch.argmax(torch.linalg.norm(M.detach(), dim=-1), dim=-1)
+        sgn = torch.sign(torch.take_along_dim(M.detach(), row[..., None, None], dim=-2).squeeze(-2))
+        out = torch.where(near_pi[..., None], axis * th[..., None] * sgn, out)
+    return out

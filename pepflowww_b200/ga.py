@@ -132,6 +132,14 @@ class GAEncoder(nn.Module):
             self._workspace = ws
         return ws
 
+    # ------------------------------------------------------------------ training path
+    def forward_autograd(self, t, rotmats_t, trans_t, angles_t, seqs_t, node_embed, edge_embed, generate_mask, res_mask):
+        """Same contract as forward(), computed by differentiable torch ops over the same parameters
+        (ga_autograd.denoiser_autograd) - the gradient path of FlowModel.forward / train_ddp.py."""
+        from .ga_autograd import denoiser_autograd
+        return denoiser_autograd(self, t, rotmats_t, trans_t, angles_t, seqs_t, node_embed, edge_embed,
+                                 generate_mask, res_mask)
+
     # ------------------------------------------------------------------ forward
     def forward(self, t, rotmats_t, trans_t, angles_t, seqs_t, node_embed, edge_embed, generate_mask, res_mask):
         """t [B,1]; rotmats_t [B,L,3,3]; trans_t [B,L,3]; angles_t [B,L,5]; seqs_t [B,L] i64;

@@ -1,0 +1,127 @@
+"""Data-parallel training harness with the reference's train_ddp.py surface (train_ddp.py:40-215; helpers
+pepflow/utils/train.py:11-53,143-155): per-rank seed `seed + 100 * rank`, DistributedDataParallel over the whole
+FlowModel (one bucketed all-reduce of the 6.88 M fp32 gradients per iteration - NCCL over NVLink on the GPU box, gloo in
+the CPU tests), weighted sum of the six losses, NaN-gradient rescue, gradient clipping, Adam + plateau scheduler, and the
+checkpoint dict {config, model, optimizer, scheduler, iteration} that inference.py:61-65 loads.
+
+SURVEY.md section 8f rank 4 / cfg5.  The forward under autograd goes through ga_autograd.denoiser_autograd (torch
+ops over the same parameters the kernels read); hand-written backward kernels are the open part of that row.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        -m pepflowww_b200.train --iters 10 --batch-size 32 --pocket 48 --peptide 12
+trains on synthetic complexes (the PepMerge LMDB is not available offline) and prints one JSON line per run."""
+import argparse
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+from torch.nn.parallel import DistributedDataParallel as DDP
+from torch.nn.utils import clip_grad_norm_
+
+
+def sum_weighted_losses(losses, weights):
+    total = 0
+    for k, v in losses.items():
+        total = total + (v if weights is None else weights[k] * v)
+    return total
+
+
+def get_optimizer(cfg, model):
+    if cfg.type == "adam":
+        return torch.optim.Adam(model.parameters(), lr=cfg.lr, weight_decay=cfg.weight_decay, betas=(cfg.beta1, cfg.beta2))
+    if cfg.type == "adamw":
+        return torch.optim.AdamW(model.parameters(), lr=cfg.lr, weight_decay=cfg.weight_decay)
+    raise NotImplementedError("Optimizer not supported: %s" % cfg.type)
+
+
+def get_scheduler(cfg, optimizer):
+    if cfg.type == "plateau":
+        return torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, factor=cfg.factor, patience=cfg.patience, min_lr=cfg.min_lr)
+    if cfg.type == "multistep":
+        return torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=cfg.milestones, gamma=cfg.gamma)
+    if cfg.type == "exp":
+        return torch.optim.lr_scheduler.ExponentialLR(optimizer, gamma=cfg.gamma)
+    raise NotImplementedError("Scheduler not supported: %s" % cfg.type)
+
+
+def train_step(model, batch, optimizer, loss_weights, max_grad_norm):
+    """One iteration of train_ddp.py:117-150.  Returns (loss, loss_dict, gradient norm before clipping)."""
+    model.train()
+    loss_dict = model(batch)
+    loss = sum_weighted_losses(loss_dict, loss_weights)
+    loss.backward()
+    for p in model.parameters():                       # rescue for NaN gradients, train_ddp.py:139-142
+        if p.grad is not None:
+            torch.nan_to_num_(p.grad, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+    grad_norm = clip_grad_norm_(model.parameters(), max_grad_norm)
+    optimizer.step()
+    optimizer.zero_grad()
+    return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}, grad_norm
+
+
+def checkpoint_dict(config, model, optimizer, scheduler, iteration):
+    return {"config": config, "model": model.state_dict(), "optimizer": optimizer.state_dict(),
+            "scheduler": scheduler.state_dict(), "iteration": iteration}
+
+
+def main(argv=None):
+    from .config import load_config
+    from .flow_model import FlowModel
+    from .pep_dataloader import synthetic_batch
+    from .utils import recursive_to, seed_all
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default=None)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--batch-size", type=int, default=None)
+    ap.add_argument("--pocket", type=int, default=48)
+    ap.add_argument("--peptide", type=int, default=12)
+    ap.add_argument("--save", default=None)
+    args = ap.parse_args(argv)
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError("pepflowww_b200.train needs a CUDA device (the loss path launches the CUDA kernels)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    config, _ = load_config(args.config) if args.config else load_config()
+    seed_all(config.train.seed + 100 * rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl")
+    net = FlowModel(config.model).to(dev)
+    model = DDP(net, device_ids=[local_rank]) if world > 1 else net
+    optimizer = get_optimizer(config.train.optimizer, model)
+    scheduler = get_scheduler(config.train.scheduler, optimizer)
+    bs = args.batch_size or config.train.batch_size
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    last = None
+    for it in range(1, args.warmup + args.iters + 1):
+        if it == args.warmup + 1:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ev0.record()
+        batch = recursive_to(synthetic_batch(bs, args.pocket, args.peptide, seed=1000 * rank + it, eight=True), dev)
+        last = train_step(model, batch, optimizer, config.train.loss_weights, config.train.max_grad_norm)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / max(1, args.iters)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        if args.save:
+            torch.save(checkpoint_dict(config, model.module if world > 1 else model, optimizer, scheduler,
+                                       args.warmup + args.iters), args.save)
+        print(json.dumps({"metric": "training samples/sec (flow-matching loss, fwd+bwd+Adam)", "unit": "samples/s",
+                          "value": bs * world / (float(ms) / 1e3), "ms_per_iter": float(ms), "n_gpus": world,
+                          "batch_per_gpu": bs, "residues": args.pocket + args.peptide, "loss": float(last[0]),
+                          "grad_norm": float(last[2]), "time": time.strftime("%Y-%m-%d %H:%M:%S")}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
