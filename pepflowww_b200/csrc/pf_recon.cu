@@ -193,11 +193,11 @@ extern "C" int pf_full_atom_reconstruction(const float* rot, const float* trans,
                                            const uint8_t* heavyatom_mask_table, float* pos14, float* R_ret,
                                            float* t_ret, uint8_t* mask_out, long long n, void* stream) {
   using namespace pf;
-  PF_REQUIRE(rot && trans && angles && aa && rigid_rot && rigid_trans && atom_group && atom_pos && pos14,
-             PF_ERR_NULL_POINTER);
-  PF_REQUIRE(!mask_out || heavyatom_mask_table, PF_ERR_NULL_POINTER);
   PF_REQUIRE(n >= 0 && n <= (long long)RC_T * 0x7fffffffLL, PF_ERR_BAD_SHAPE);
-  if (n == 0) return PF_OK;
+  PF_REQUIRE(rigid_rot && rigid_trans && atom_group && atom_pos, PF_ERR_NULL_POINTER);
+  if (n == 0) return PF_OK;   // empty batch: the data pointers of empty tensors are NULL
+  PF_REQUIRE(rot && trans && angles && aa && pos14, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(!mask_out || heavyatom_mask_table, PF_ERR_NULL_POINTER);
   FullAtomArgs a{rot, trans, angles, aa, rigid_rot, rigid_trans, atom_group, atom_pos, heavyatom_mask_table,
                  pos14, R_ret, t_ret, mask_out, n};
   full_atom_kernel<<<(unsigned)((n + RC_T - 1) / RC_T), RC_T, 0, as_stream(stream)>>>(a);
@@ -209,9 +209,10 @@ extern "C" int pf_reconstruct_backbone(const float* rot, const float* trans, con
                                        const int64_t* res_nb, const uint8_t* mask, const float* bb_coords,
                                        const float* bb_oxygen, float* pos_bb, int N, int L, void* stream) {
   using namespace pf;
-  PF_REQUIRE(rot && trans && aa && chain_nb && res_nb && mask && bb_coords && bb_oxygen && pos_bb, PF_ERR_NULL_POINTER);
   PF_REQUIRE(N >= 0 && L >= 0, PF_ERR_BAD_SHAPE);
+  PF_REQUIRE(bb_coords && bb_oxygen, PF_ERR_NULL_POINTER);
   if (N == 0 || L == 0) return PF_OK;
+  PF_REQUIRE(rot && trans && aa && chain_nb && res_nb && mask && pos_bb, PF_ERR_NULL_POINTER);
   BackboneArgs a{rot, trans, aa, chain_nb, res_nb, mask, bb_coords, bb_oxygen, pos_bb, N, L};
   const long long n = (long long)N * L;
   backbone_kernel<<<(unsigned)((n + RC_T - 1) / RC_T), RC_T, 0, as_stream(stream)>>>(a);
