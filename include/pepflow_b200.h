@@ -261,6 +261,15 @@ int pf_reconstruct_backbone(const float* rot, const float* trans, const int64_t*
                             const int64_t* res_nb, const uint8_t* mask, const float* bb_coords,
                             const float* bb_oxygen, float* pos_bb, int N, int L, void* stream);
 
+/* get_torsion_angle, models_con/torsion.py:13-66 (the inverse of pf_full_atom_reconstruction; the dataset builder
+ * stores its outputs as torsion_angle / torsion_angle_mask): pos_atoms[n,atoms_in,3] (atoms_in = 14 or 15, atom14
+ * slot order), aa[n] i64 -> torsion[n,5] = (psi from N, CA, C, O; chi1..chi4) in [0, 2 pi), 0 where undefined, and
+ * torsion_mask[n,5] u8 (angle exists for the residue type and its four atoms are not degenerate).  Residue types
+ * outside 0..19 give zeros / false (:52-58).  chi_atoms[21,4,4] i32: atom14 slots of the defining atoms, -1 = no such
+ * angle (pepflow/modules/protein/constants.py:372-400).                                                          */
+int pf_torsion_angles(const float* pos_atoms, const int64_t* aa, const int32_t* chi_atoms, float* torsion,
+                      uint8_t* torsion_mask, long long n, int atoms_in, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

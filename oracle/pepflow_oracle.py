@@ -634,3 +634,30 @@ def flow_losses(sd, batch, noise, torsions_mask, cfg_min_clip=0.9, sigma=1.0, K=
     torsion_loss = (((vec(pa) - vec(a1)) ** 2 * aml).sum((-1, -2)) / asum).mean()                    # :213-218
     return {"trans_loss": trans_loss, "rot_loss": rot_loss, "bb_atom_loss": bb_loss, "seqs_loss": seqs_loss,
             "angle_loss": angle_loss, "torsion_loss": torsion_loss}
+
+
+def _torsion_raw(p0, p1, p2, p3):
+    """models_con/torsion.py:13-29 (_get_torsion): like dihedral() but degenerate geometry stays NaN."""
+    v0, v1, v2 = p2 - p1, p0 - p1, p3 - p2
+    u1 = torch.cross(v0, v1, dim=-1)
+    n1 = u1 / torch.linalg.norm(u1, dim=-1, keepdim=True)
+    u2 = torch.cross(v0, v2, dim=-1)
+    n2 = u2 / torch.linalg.norm(u2, dim=-1, keepdim=True)
+    sgn = torch.sign((torch.cross(v1, v2, dim=-1) * v0).sum(-1))
+    return sgn * torch.acos((n1 * n2).sum(-1).clamp(-0.999999, 0.999999))
+
+
+def torsion_angles(tables, pos, aa):
+    """get_torsion_angle, models_con/torsion.py:31-66, vectorised over residues: pos [..., A, 3], aa [...] ->
+    (torsion [..., 5] in [0, 2 pi), mask [..., 5]).  psi = torsion(N, CA, C, O); chi_i from tables['chi_atoms']."""
+    known = (aa >= 0) & (aa < 20)
+    idx = tables["chi_atoms"][aa.clamp(0, 20)].long()                    # [..., 4, 4]
+    have = (idx[..., 0] >= 0) & known[..., None]
+    g = lambda j: torch.gather(pos, -2, idx[..., j].clamp(min=0)[..., None].expand(idx.shape[:-1] + (3,)))
+    chi = _torsion_raw(g(0), g(1), g(2), g(3))
+    chi = torch.where(have, chi, torch.full_like(chi, float("inf")))
+    psi = _torsion_raw(pos[..., 0, :], pos[..., 1, :], pos[..., 2, :], pos[..., 3, :])
+    tor = torch.cat([psi[..., None], chi], dim=-1)
+    mask = torch.isfinite(tor) & known[..., None]
+    tor = torch.where(mask, tor, torch.zeros_like(tor)) % TWO_PI
+    return tor, mask

@@ -58,6 +58,7 @@ SIGNATURES = {
     "pf_node_embed": (_i, [_p] * 16 + [_i] * 3 + [_p]),
     "pf_full_atom_reconstruction": (_i, [_p] * 13 + [C.c_longlong, _p]),
     "pf_reconstruct_backbone": (_i, [_p] * 9 + [_i] * 2 + [_p]),
+    "pf_torsion_angles": (_i, [_p] * 5 + [C.c_longlong, _i, _p]),
 }
 
 # enum sizes of include/pepflow_b200.h

@@ -86,7 +86,7 @@ _RIGID_TABLES = {}
 
 def rigid_tables(device="cpu"):
     """dict of tensors on `device`: rigid_rot [21,8,3,3], rigid_trans [21,8,3], atom_group [21,14] i32,
-    atom_pos [21,14,3], bb_coords [21,3,3], bb_oxygen [21,3], heavyatom_mask [22,15] u8."""
+    atom_pos [21,14,3], bb_coords [21,3,3], bb_oxygen [21,3], chi_atoms [21,4,4] i32, heavyatom_mask [22,15] u8."""
     import os
 
     import numpy as np

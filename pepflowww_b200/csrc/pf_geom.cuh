@@ -4,8 +4,8 @@
 
 namespace pf {
 
-// geometry.py:296-313: signed dihedral of four points, NaN (degenerate geometry, e.g. padded residues) -> 0
-__device__ __forceinline__ float dihedral4(const float* p0, const float* p1, const float* p2, const float* p3) {
+// Signed dihedral of four points, NaN for degenerate geometry (models_con/torsion.py:13-29, _get_torsion).
+__device__ __forceinline__ float dihedral4_raw(const float* p0, const float* p1, const float* p2, const float* p3) {
   const float v0x = p2[0] - p1[0], v0y = p2[1] - p1[1], v0z = p2[2] - p1[2];
   const float v1x = p0[0] - p1[0], v1y = p0[1] - p1[1], v1z = p0[2] - p1[2];
   const float v2x = p3[0] - p2[0], v2y = p3[1] - p2[1], v2z = p3[2] - p2[2];
@@ -13,11 +13,17 @@ __device__ __forceinline__ float dihedral4(const float* p0, const float* p1, con
   const float u2x = v0y * v2z - v0z * v2y, u2y = v0z * v2x - v0x * v2z, u2z = v0x * v2y - v0y * v2x;
   const float l1 = sqrtf(u1x * u1x + u1y * u1y + u1z * u1z), l2 = sqrtf(u2x * u2x + u2y * u2y + u2z * u2z);
   const float d = (u1x / l1) * (u2x / l2) + (u1y / l1) * (u2y / l2) + (u1z / l1) * (u2z / l2);
-  if (!(d == d)) return 0.f;                       // nan_to_num
+  if (!(d == d)) return d;                         // fminf / fmaxf would swallow the NaN
   const float cx = v1y * v2z - v1z * v2y, cy = v1z * v2x - v1x * v2z, cz = v1x * v2y - v1y * v2x;
   const float s = cx * v0x + cy * v0y + cz * v0z;
   const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
   return sg * acosf(fminf(fmaxf(d, -0.999999f), 0.999999f));
+}
+
+// geometry.py:296-313: the same with nan_to_num (degenerate geometry, e.g. padded residues -> 0)
+__device__ __forceinline__ float dihedral4(const float* p0, const float* p1, const float* p2, const float* p3) {
+  const float a = dihedral4_raw(p0, p1, p2, p3);
+  return a == a ? a : 0.f;
 }
 
 // C = A B for row-major 3x3 matrices

@@ -1,24 +1,29 @@
 // Post-sampling reconstruction: the step right after FlowModel.sample in the reference's
-// sampling scripts (models_con/sample.py:46,77,105-108).
+// sampling scripts (models_con/sample.py:46,77,105-108), and its inverse on the data side.
 //
 //   pf_full_atom_reconstruction  models_con/torsion.py:140-226 (+ _make_psi_chi_rotation_matrices :68-96,
 //                                _get_rigid_group :99-113, get_heavyatom_mask :126-138): backbone frames + 5 torsions +
 //                                residue types -> atom14 coordinates, the psi / chi1-4 frames, heavy-atom mask
 //   pf_reconstruct_backbone      pepflow/modules/common/geometry.py:446-489: backbone frames + residue types ->
 //                                N, CA, C, O (psi measured on the rebuilt backbone of residues i and i + 1)
+//   pf_torsion_angles            models_con/torsion.py:13-66 (get_torsion_angle: psi + chi1-4 and their mask from
+//                                atom14 coordinates) - what the dataset builder stores as torsion_angle / _mask
 //
-// Both are O(residues) and HBM / latency bound: ~70 floats in, up to 129 floats out per residue.  A CTA takes 128
-// consecutive residues: one thread composes the frame chain of one residue (the products are associated exactly as
-// the reference's compose_chain does it: the last two factors first), parks the six frames in shared memory, then the
-// whole CTA walks the flat output arrays so every HBM store is a run of consecutive addresses.
+// All three are O(residues) and HBM bound: 76 B in, 183 - 471 B out per residue.  The first version issued one strided
+// scalar load per thread and element (226 M L1 sectors for 8 M sectors of data: L1TEX 95 % busy, DRAM 23 %); now a CTA
+// takes a tile of 128 consecutive residues, moves its inputs into shared memory with coalesced loads, keeps the
+// per-residue-type constant tables in shared memory, lets one thread compose the frame chain of one residue (products
+// associated exactly as the reference's compose_chain does it: the last two factors first), and then the whole CTA walks
+// the flat output arrays one element per thread, so every HBM store instruction writes consecutive addresses.
 #include "pf_common.cuh"
 #include "pf_geom.cuh"
 
 namespace pf {
 
-constexpr int RC_T = 128;          // threads = residues per CTA
+constexpr int RC_T = 128;          // threads = residues per tile
 constexpr int RC_FR = 6;           // frames kept per residue: backbone, psi, chi1..chi4
 constexpr int RC_FW = 12;          // floats per frame: R (9, row-major) | t (3)
+constexpr int RC_ROW = RC_FR * RC_FW + 1;   // +1: residue rows start on distinct banks
 constexpr int RC_NAA = 21;         // rows of the rigid-group tables (20 residue types + UNK)
 
 struct FullAtomArgs {
@@ -47,80 +52,112 @@ __device__ __forceinline__ void torsion_frame(const float* Rp, const float* tp, 
 }
 
 __global__ void __launch_bounds__(RC_T) full_atom_kernel(FullAtomArgs a) {
-  __shared__ float s_fr[RC_T][RC_FR * RC_FW + 1];   // +1: residue rows on distinct banks
+  __shared__ float s_fr[RC_T][RC_ROW];              // per residue: six frames; on entry rot | trans | torsions
+  __shared__ float s_grp[RC_NAA * 5 * RC_FW];       // rigid groups 3..7 (psi, chi1..chi4) per type: R | t
+  __shared__ float s_apos[RC_NAA * 14 * 3];
+  __shared__ uint8_t s_agrp[RC_NAA * 14 + 2];
+  __shared__ uint8_t s_mtab[22 * 15 + 2];
   __shared__ int s_aa[RC_T];
   const int tid = threadIdx.x;
-  const long long base = (long long)blockIdx.x * RC_T;
-  const int rows = (int)min((long long)RC_T, a.n - base);
-  if (tid < rows) {
-    const long long r = base + tid;
-    const long long aa64 = a.aa[r];
-    // rows outside the 21-row tables (PAD = 21, negatives) have no rigid groups: they collapse onto the backbone origin
-    const int aa = (aa64 >= 0 && aa64 < RC_NAA) ? (int)aa64 : -1;
-    s_aa[tid] = (aa64 >= 0 && aa64 < 22) ? (int)aa64 : -1;
-    float* F = s_fr[tid];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) F[k] = a.rot[r * 9 + k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) F[9 + k] = a.trans[r * 3 + k];
-    float ang[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) ang[k] = a.angles[r * 5 + k];
-    // rigid groups: 3 psi, 4..7 chi1..chi4; parents: psi and chi1 hang off the backbone, chi_k off chi_{k-1}
-#pragma unroll
-    for (int f = 1; f < RC_FR; ++f) {
-      const int g = f + 2, parent = (f <= 2) ? 0 : f - 1;
-      float Rg[9], tg[3];
-      if (aa >= 0) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Rg[k] = __ldg(a.rigid_rot + ((size_t)aa * 8 + g) * 9 + k);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) tg[k] = __ldg(a.rigid_trans + ((size_t)aa * 8 + g) * 3 + k);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Rg[k] = 0.f;
-        tg[0] = tg[1] = tg[2] = 0.f;
-      }
-      float Rp[9], tp[3];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) Rp[k] = F[parent * RC_FW + k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) tp[k] = F[parent * RC_FW + 9 + k];
-      torsion_frame(Rp, tp, Rg, tg, ang[f - 1], F + f * RC_FW, F + f * RC_FW + 9);
-    }
+  // ---- constant tables: once per (persistent) CTA
+  for (int e = tid; e < RC_NAA * 5 * RC_FW; e += RC_T) {
+    const int aa = e / (5 * RC_FW), k = e - aa * (5 * RC_FW), g = 3 + k / RC_FW, c = k % RC_FW;
+    s_grp[e] = c < 9 ? a.rigid_rot[(aa * 8 + g) * 9 + c] : a.rigid_trans[(aa * 8 + g) * 3 + (c - 9)];
   }
-  __syncthreads();
-  // ---- atom14 positions: one (residue, slot) per thread and trip
-  for (int e = tid; e < rows * 14; e += RC_T) {
-    const int r = e / 14, s = e - r * 14, aa = s_aa[r];
-    float p[3] = {0.f, 0.f, 0.f};
-    int f = 0;
-    if (aa >= 0 && aa < RC_NAA) {
-      const int g = __ldg(a.atom_group + aa * 14 + s);
-      f = g < 3 ? 0 : g - 2;   // backbone / omega / phi groups all carry the backbone frame (torsion.py:214-215)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) p[k] = __ldg(a.atom_pos + ((size_t)aa * 14 + s) * 3 + k);
-    }
-    float q[3];
-    rigid_apply(s_fr[r] + f * RC_FW, s_fr[r] + f * RC_FW + 9, p, q);
-    float* o = a.pos14 + (base * 14 + e) * 3;
-    o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
-  }
-  if (a.R_ret)
-    for (int e = tid; e < rows * RC_FR * 9; e += RC_T) {
-      const int r = e / (RC_FR * 9), k = e - r * (RC_FR * 9);
-      a.R_ret[base * (RC_FR * 9) + e] = s_fr[r][(k / 9) * RC_FW + k % 9];
-    }
-  if (a.t_ret)
-    for (int e = tid; e < rows * RC_FR * 3; e += RC_T) {
-      const int r = e / (RC_FR * 3), k = e - r * (RC_FR * 3);
-      a.t_ret[base * (RC_FR * 3) + e] = s_fr[r][(k / 3) * RC_FW + 9 + k % 3];
-    }
+  for (int e = tid; e < RC_NAA * 14 * 3; e += RC_T) s_apos[e] = a.atom_pos[e];
+  for (int e = tid; e < RC_NAA * 14; e += RC_T) s_agrp[e] = (uint8_t)a.atom_group[e];
   if (a.mask_out)
-    for (int e = tid; e < rows * 15; e += RC_T) {
-      const int r = e / 15, s = e - r * 15, aa = s_aa[r];
-      a.mask_out[base * 15 + e] = aa >= 0 ? __ldg(a.mask_table + aa * 15 + s) : (uint8_t)0;
+    for (int e = tid; e < 22 * 15; e += RC_T) s_mtab[e] = a.mask_table[e];
+  const long long tiles = (a.n + RC_T - 1) / RC_T;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long base = tile * RC_T;
+    const int rows = (int)min((long long)RC_T, a.n - base);
+    __syncthreads();   // tables visible / previous tile's readers done
+    // ---- inputs, coalesced: rot -> F[0..8], trans -> F[9..11], torsions -> F[12..16] (consumed before frame 1 lands)
+    for (int e = tid; e < rows * 9; e += RC_T) s_fr[e / 9][e % 9] = a.rot[base * 9 + e];
+    for (int e = tid; e < rows * 3; e += RC_T) s_fr[e / 3][9 + e % 3] = a.trans[base * 3 + e];
+    for (int e = tid; e < rows * 5; e += RC_T) s_fr[e / 5][12 + e % 5] = a.angles[base * 5 + e];
+    if (tid < rows) {
+      const long long aa64 = a.aa[base + tid];
+      // 0..20: table rows; 21 (PAD): no rigid groups, zero mask row; anything else: nothing at all
+      s_aa[tid] = (aa64 >= 0 && aa64 < 22) ? (int)aa64 : -1;
     }
+    __syncthreads();
+    if (tid < rows) {
+      float* F = s_fr[tid];
+      const int aa = s_aa[tid];
+      float ang[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) ang[k] = F[12 + k];
+      // rigid groups: 3 psi, 4..7 chi1..chi4; parents: psi and chi1 hang off the backbone, chi_k off chi_{k-1}
+#pragma unroll
+      for (int f = 1; f < RC_FR; ++f) {
+        const int parent = (f <= 2) ? 0 : f - 1;
+        float Rg[9], tg[3], Rp[9], tp[3];
+        if (aa >= 0 && aa < RC_NAA) {
+          const float* G = s_grp + (aa * 5 + (f - 1)) * RC_FW;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Rg[k] = G[k];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) tg[k] = G[9 + k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Rg[k] = 0.f;
+          tg[0] = tg[1] = tg[2] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rp[k] = F[parent * RC_FW + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tp[k] = F[parent * RC_FW + 9 + k];
+        torsion_frame(Rp, tp, Rg, tg, ang[f - 1], F + f * RC_FW, F + f * RC_FW + 9);
+      }
+    }
+    __syncthreads();
+    // ---- atom14 coordinates: one output float per thread and trip (residue r, slot s, axis k)
+    for (int e = tid; e < rows * 42; e += RC_T) {
+      const int r = e / 42, c = e - r * 42, s = c / 3, k = c - s * 3, aa = s_aa[r];
+      float px = 0.f, py = 0.f, pz = 0.f;
+      int f = 0;
+      if (aa >= 0 && aa < RC_NAA) {
+        const int g = s_agrp[aa * 14 + s];
+        f = g < 3 ? 0 : g - 2;   // backbone / omega / phi groups all carry the backbone frame (torsion.py:214-215)
+        const float* P = s_apos + (aa * 14 + s) * 3;
+        px = P[0]; py = P[1]; pz = P[2];
+      }
+      const float* Fr = s_fr[r] + f * RC_FW;
+      a.pos14[base * 42 + e] = fmaf(Fr[k * 3 + 2], pz, fmaf(Fr[k * 3 + 1], py, Fr[k * 3] * px)) + Fr[9 + k];
+    }
+    if (a.R_ret)
+      for (int e = tid; e < rows * RC_FR * 9; e += RC_T) {
+        const int r = e / (RC_FR * 9), k = e - r * (RC_FR * 9);
+        a.R_ret[base * (RC_FR * 9) + e] = s_fr[r][(k / 9) * RC_FW + k % 9];
+      }
+    if (a.t_ret)
+      for (int e = tid; e < rows * RC_FR * 3; e += RC_T) {
+        const int r = e / (RC_FR * 3), k = e - r * (RC_FR * 3);
+        a.t_ret[base * (RC_FR * 3) + e] = s_fr[r][(k / 3) * RC_FW + 9 + k % 3];
+      }
+    if (a.mask_out) {
+      // four mask bytes per thread and store; base * 15 is a multiple of 4 (base is a multiple of 128)
+      const int words = (rows * 15 + 3) / 4;
+      for (int w = tid; w < words; w += RC_T) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = w * 4 + j;
+          if (e < rows * 15) {
+            const int r = e / 15, aa = s_aa[r];
+            v |= (uint32_t)(aa >= 0 ? s_mtab[aa * 15 + (e - r * 15)] : 0) << (8 * j);
+          }
+        }
+        if (w * 4 + 3 < rows * 15) {
+          reinterpret_cast<uint32_t*>(a.mask_out + base * 15)[w] = v;
+        } else {
+          for (int j = 0; j < 4 && w * 4 + j < rows * 15; ++j) a.mask_out[base * 15 + w * 4 + j] = (uint8_t)(v >> (8 * j));
+        }
+      }
+    }
+  }
 }
 
 __device__ __forceinline__ int clamp_aa(int64_t v) { return v < 0 ? 0 : (v > 20 ? 20 : (int)v); }
@@ -132,22 +169,30 @@ struct BackboneArgs {
 };
 
 __global__ void __launch_bounds__(RC_T) backbone_kernel(BackboneArgs a) {
+  __shared__ float s_in[RC_T + 1][13];     // rot | trans of the tile's residues and the one after it
   __shared__ float s_out[RC_T][13];
+  __shared__ float s_tab[RC_NAA * 12];     // N, CA, C (backbone frame) | O (psi frame) per residue type
   const int tid = threadIdx.x;
   const long long n = (long long)a.N * a.L;
   const long long base = (long long)blockIdx.x * RC_T;
   const int rows = (int)min((long long)RC_T, n - base);
+  const int rows_in = (int)min((long long)RC_T + 1, n - base);
+  for (int e = tid; e < RC_NAA * 12; e += RC_T) {
+    const int aa = e / 12, c = e - aa * 12;
+    s_tab[e] = c < 9 ? a.bb_coords[aa * 9 + c] : a.bb_oxygen[aa * 3 + (c - 9)];
+  }
+  for (int e = tid; e < rows_in * 9; e += RC_T) s_in[e / 9][e % 9] = a.rot[base * 9 + e];
+  for (int e = tid; e < rows_in * 3; e += RC_T) s_in[e / 3][9 + e % 3] = a.trans[base * 3 + e];
+  __syncthreads();
   if (tid < rows) {
     const long long r = base + tid;
     const int l = (int)(r % a.L);
-    float R[9], t[3], bb[9];
+    const float* R = s_in[tid];
+    const float* t = R + 9;
+    const int aa = clamp_aa(a.aa[r]);                                     // geometry.py:462
+    float bb[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = a.rot[r * 9 + k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) t[k] = a.trans[r * 3 + k];
-    const int aa = clamp_aa(a.aa[r]);   // geometry.py:462
-#pragma unroll
-    for (int k = 0; k < 3; ++k) rigid_apply(R, t, a.bb_coords + (size_t)aa * 9 + k * 3, bb + k * 3);
+    for (int k = 0; k < 3; ++k) rigid_apply(R, t, s_tab + aa * 12 + k * 3, bb + k * 3);
     // psi_i = dihedral(N_i, CA_i, C_i, N_{i+1}) when i+1 continues the chain (geometry.py:355-390, topology.py:5-24)
     float psi = 0.f;
     if (l + 1 < a.L) {
@@ -155,12 +200,8 @@ __global__ void __launch_bounds__(RC_T) backbone_kernel(BackboneArgs a) {
       d = d < 0 ? -d : d;
       if (d == 1 && a.chain_nb[r + 1] == a.chain_nb[r] && a.mask[r]) {
         const int aa1 = clamp_aa(a.aa[r + 1]);
-        float R1[9], t1[3], n1[3];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) R1[k] = a.rot[(r + 1) * 9 + k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) t1[k] = a.trans[(r + 1) * 3 + k];
-        rigid_apply(R1, t1, a.bb_coords + (size_t)aa1 * 9, n1);
+        float n1[3];
+        rigid_apply(s_in[tid + 1], s_in[tid + 1] + 9, s_tab + aa1 * 12, n1);
         psi = dihedral4(bb, bb + 3, bb + 6, n1);
       }
     }
@@ -175,7 +216,7 @@ __global__ void __launch_bounds__(RC_T) backbone_kernel(BackboneArgs a) {
       M[i * 3 + 2] = fmaf(R[i * 3 + 2], c, -(R[i * 3 + 1] * s));
     }
     float o[3];
-    rigid_apply(M, t, a.bb_oxygen + (size_t)aa * 3, o);
+    rigid_apply(M, t, s_tab + aa * 12 + 9, o);
 #pragma unroll
     for (int k = 0; k < 9; ++k) s_out[tid][k] = bb[k];
 #pragma unroll
@@ -183,6 +224,58 @@ __global__ void __launch_bounds__(RC_T) backbone_kernel(BackboneArgs a) {
   }
   __syncthreads();
   for (int e = tid; e < rows * 12; e += RC_T) a.pos_bb[base * 12 + e] = s_out[e / 12][e % 12];
+}
+
+// ---- torsions from coordinates -------------------------------------------------------------------------------------
+constexpr int TA_MAXA = 15;                 // atoms per residue the staging tile can hold
+
+struct TorsionArgs {
+  const float* pos; const int64_t* aa; const int32_t* chi_atoms; float* torsion; uint8_t* mask;
+  long long n; int A;
+};
+
+__global__ void __launch_bounds__(RC_T) torsion_angles_kernel(TorsionArgs a) {
+  __shared__ float s_pos[RC_T][TA_MAXA * 3 + 1];
+  __shared__ int8_t s_chi[RC_NAA * 16];
+  __shared__ float s_val[RC_T * 5];
+  __shared__ uint8_t s_msk[RC_T * 5];
+  const int tid = threadIdx.x;
+  const long long base = (long long)blockIdx.x * RC_T;
+  const int rows = (int)min((long long)RC_T, a.n - base);
+  const int W = a.A * 3;
+  for (int e = tid; e < RC_NAA * 16; e += RC_T) s_chi[e] = (int8_t)a.chi_atoms[e];
+  for (int e = tid; e < rows * W; e += RC_T) s_pos[e / W][e % W] = a.pos[base * W + e];
+  __syncthreads();
+  if (tid < rows) {
+    const long long aa64 = a.aa[base + tid];
+    const float* P = s_pos[tid];
+    float v[5];
+    bool ok[5];
+    if (aa64 >= 0 && aa64 < 20) {                                   // torsion.py:52: 0..19 only
+      v[0] = dihedral4_raw(P, P + 3, P + 6, P + 9);                 // "af style psi": N, CA, C, O (:44-45)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int8_t* q = s_chi + (int)aa64 * 16 + i * 4;
+        v[1 + i] = q[0] >= 0 ? dihedral4_raw(P + q[0] * 3, P + q[1] * 3, P + q[2] * 3, P + q[3] * 3)
+                             : __int_as_float(0x7f800000);          // no such angle: +inf (:32)
+      }
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        ok[i] = isfinite(v[i]);                                     // :56 isfinite, :60 nan_to_num(posinf=0), :63 % 2 pi
+        v[i] = ok[i] ? mod_2pi(v[i]) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { v[i] = 0.f; ok[i] = false; }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { s_val[tid * 5 + i] = v[i]; s_msk[tid * 5 + i] = ok[i] ? 1 : 0; }
+  }
+  __syncthreads();
+  for (int e = tid; e < rows * 5; e += RC_T) {
+    a.torsion[base * 5 + e] = s_val[e];
+    a.mask[base * 5 + e] = s_msk[e];
+  }
 }
 
 }  // namespace pf
@@ -198,9 +291,13 @@ extern "C" int pf_full_atom_reconstruction(const float* rot, const float* trans,
   if (n == 0) return PF_OK;   // empty batch: the data pointers of empty tensors are NULL
   PF_REQUIRE(rot && trans && angles && aa && pos14, PF_ERR_NULL_POINTER);
   PF_REQUIRE(!mask_out || heavyatom_mask_table, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(!mask_out || (reinterpret_cast<uintptr_t>(mask_out) & 3u) == 0, PF_ERR_MISALIGNED);
   FullAtomArgs a{rot, trans, angles, aa, rigid_rot, rigid_trans, atom_group, atom_pos, heavyatom_mask_table,
                  pos14, R_ret, t_ret, mask_out, n};
-  full_atom_kernel<<<(unsigned)((n + RC_T - 1) / RC_T), RC_T, 0, as_stream(stream)>>>(a);
+  // persistent CTAs (4 fit on an SM next to their 46 KB of shared memory): the constant tables are staged once per CTA
+  const long long tiles = (n + RC_T - 1) / RC_T;
+  const unsigned grid = (unsigned)min(tiles, (long long)num_sms() * 4);
+  full_atom_kernel<<<grid, RC_T, 0, as_stream(stream)>>>(a);
   PF_CHECK_LAUNCH();
   return PF_OK;
 }
@@ -216,6 +313,19 @@ extern "C" int pf_reconstruct_backbone(const float* rot, const float* trans, con
   BackboneArgs a{rot, trans, aa, chain_nb, res_nb, mask, bb_coords, bb_oxygen, pos_bb, N, L};
   const long long n = (long long)N * L;
   backbone_kernel<<<(unsigned)((n + RC_T - 1) / RC_T), RC_T, 0, as_stream(stream)>>>(a);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+extern "C" int pf_torsion_angles(const float* pos_atoms, const int64_t* aa, const int32_t* chi_atoms, float* torsion,
+                                 uint8_t* torsion_mask, long long n, int atoms_in, void* stream) {
+  using namespace pf;
+  PF_REQUIRE(n >= 0 && n <= (long long)RC_T * 0x7fffffffLL && atoms_in >= 14 && atoms_in <= TA_MAXA, PF_ERR_BAD_SHAPE);
+  PF_REQUIRE(chi_atoms, PF_ERR_NULL_POINTER);
+  if (n == 0) return PF_OK;
+  PF_REQUIRE(pos_atoms && aa && torsion && torsion_mask, PF_ERR_NULL_POINTER);
+  TorsionArgs a{pos_atoms, aa, chi_atoms, torsion, torsion_mask, n, atoms_in};
+  torsion_angles_kernel<<<(unsigned)((n + RC_T - 1) / RC_T), RC_T, 0, as_stream(stream)>>>(a);
   PF_CHECK_LAUNCH();
   return PF_OK;
 }

@@ -282,3 +282,16 @@ def reconstruct_backbone(rot, trans, aa, chain_nb, res_nb, mask, tables):
                                       ptr(_c(res_nb, I64), I64), ptr(m, U8), ptr(tables["bb_coords"]),
                                       ptr(tables["bb_oxygen"]), ptr(out), B, L, stream()))
     return out
+
+
+def torsion_angles(pos_atoms, aa, tables):
+    """get_torsion_angle (models_con/torsion.py:49-66) for every residue of pos_atoms [..., A, 3] / aa [...] in one
+    launch (pf_torsion_angles): (torsion [..., 5] in [0, 2 pi), mask [..., 5] bool)."""
+    lib = _lib.lib_for(pos_atoms.device)
+    pos = _c(pos_atoms)
+    n = aa.numel()
+    tor = torch.empty(*aa.shape, 5, device=pos.device, dtype=F32)
+    mask = torch.empty(*aa.shape, 5, device=pos.device, dtype=U8)
+    check(lib.pf_torsion_angles(ptr(pos), ptr(_c(aa, I64), I64), ptr(tables["chi_atoms"], torch.int32), ptr(tor),
+                                ptr(mask, U8), n, pos.shape[-2], stream()))
+    return tor, mask.view(torch.bool)

@@ -35,6 +35,16 @@ def get_heavyatom_mask(aa):
     return restype_to_heavyatom_masks.to(aa.device)[aa.flatten()].reshape(*aa.shape, 15)
 
 
+def get_torsion_angle(pos14, aa):
+    """(torsion [..., 5], torsion_mask [..., 5]): psi (N, CA, C, O) and chi1-4 in [0, 2 pi) from atom14 coordinates
+    pos14 [..., A >= 14, 3] and residue types aa [...] (models_con/torsion.py:49-66, there one residue at a time in a
+    Python loop); one launch of pf_torsion_angles for the whole batch."""
+    _require_cuda("get_torsion_angle", pos14)
+    if pos14.shape[:-2] != aa.shape or pos14.shape[-1] != 3 or not 14 <= pos14.shape[-2] <= 15:
+        raise ValueError("get_torsion_angle: shapes must be pos14 [..., 14|15, 3], aa [...]")
+    return ops.torsion_angles(pos14, aa, constants.rigid_tables(pos14.device))
+
+
 def reconstruct_side_chains(samples):
     """pos_ha [B,N,15,3] and mask [B,N,15] from the last trajectory entry of FlowModel.sample - what
     save_samples_sc does before writing PDB files (models_con/sample.py:105-108) - in one launch."""

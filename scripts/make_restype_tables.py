@@ -12,6 +12,8 @@ reference builds at import time (pepflow/modules/protein/constants.py:665-668 fi
   atom_pos    [21, 14, 3]   f32  position of the slot in its group's frame
   bb_coords   [21, 3, 3]    f32  N, CA, C in the backbone frame
   bb_oxygen   [21, 3]       f32  O in the psi frame
+  chi_atoms   [21, 4, 4]    i32  atom14 slots of the four atoms that define chi1..chi4 (-1: the angle does not exist;
+                                 constants.py:372-400 looked up through restype_atom14_name_to_index :150-155)
 Row 20 (UNK) is zero everywhere except bb_* which the reference fills for every row it has data for.
 """
 import os
@@ -37,6 +39,11 @@ def main():
         bb_coords=C.backbone_atom_coordinates_tensor.numpy().astype(np.float32),
         bb_oxygen=C.bb_oxygen_coordinate_tensor.numpy().astype(np.float32),
     )
+    chi = np.full((21, 4, 4), -1, dtype=np.int32)
+    for aa in range(21):
+        for i, names in enumerate(C.chi_angles_atoms[C.AA(aa)] if C.AA(aa) in C.chi_angles_atoms else []):
+            chi[aa, i] = [C.restype_atom14_name_to_index[C.AA(aa)][n] for n in names]
+    out["chi_atoms"] = chi
     assert out["rigid_rot"].shape == (21, 8, 3, 3) and out["atom_group"].max() <= 7
     path = os.path.join(ROOT, "pepflowww_b200", "data", "restype_rigid_tables.npz")
     np.savez_compressed(path, **out)

@@ -49,7 +49,14 @@ def main():
     pos14, R_ret, t_ret = torsion.full_atom_reconstruction(R, t, angles, aa)
     mask15 = torsion.get_heavyatom_mask(aa)
     pos_bb = geometry.reconstruct_backbone(R, t, aa, chain_nb, res_nb, mask)
-    save("reconstruction", R=R, t=t, angles=angles, aa=aa, chain_nb=chain_nb, res_nb=res_nb, mask=mask,
+    # the inverse map, one complex at a time as the dataset builder calls it (models_con/torsion.py:49-66); a second
+    # input with degenerate side chains (all atoms of some residues collapsed onto CA) exercises the NaN -> mask path
+    tor = [torsion.get_torsion_angle(pos14[b], aa[b]) for b in range(B)]
+    pos_deg = pos14.clone()
+    pos_deg[0, 3:9, 4:] = pos_deg[0, 3:9, 1:2]
+    tor_deg = torsion.get_torsion_angle(pos_deg[0], aa[0])
+    save("reconstruction", torsion=torch.stack([x[0] for x in tor]), torsion_mask=torch.stack([x[1] for x in tor]),
+         pos_deg=pos_deg[0], torsion_deg=tor_deg[0], torsion_mask_deg=tor_deg[1], R=R, t=t, angles=angles, aa=aa, chain_nb=chain_nb, res_nb=res_nb, mask=mask,
          pos14=pos14, R_ret=R_ret, t_ret=t_ret, mask15=mask15, pos_bb=pos_bb)
 
 

@@ -618,6 +618,25 @@ def test_reconstruction_kernels(dev):
           % (e_gold, e_bb, e_big, e_bb_big, float(dO.max()), float(dO.median()), e_equiv, e_equiv_bb))
     assert max(e_gold, e_bb, e_big, e_bb_big, e_equiv) < 1e-5
     assert float(dO.median()) < 1e-4 and float(dO.quantile(0.999)) < 2e-3 and e_equiv_bb < 2e-3
+    # ---- the inverse map: pf_torsion_angles (get_torsion_angle) against the reference's outputs, incl. collapsed side
+    # chains (NaN -> masked), and the round trip reconstruct -> measure at bench scale: chi comes back as it went in,
+    # psi shifted by pi (the reference measures N-CA-C-O without AlphaFold's psi mirror), masks = torsions_mask[aa]
+    tor, tm = torsion.get_torsion_angle(c("pos14"), c("aa"))
+    assert circ_err(tor.cpu(), g["torsion"]) < 1e-5 and (tm.cpu() == g["torsion_mask"]).all()
+    tor, tm = torsion.get_torsion_angle(c("pos_deg"), c("aa")[0])
+    assert circ_err(tor.cpu(), g["torsion_deg"]) < 1e-5 and (tm.cpu() == g["torsion_mask_deg"]).all()
+    tor15, _ = torsion.get_torsion_angle(torch.nn.functional.pad(c("pos14"), (0, 0, 0, 1)), c("aa"))
+    assert circ_err(tor15.cpu(), g["torsion"]) < 1e-5                      # 15-slot layout of the batch schema
+    rt, rt_mask = torsion.get_torsion_angle(k_pos, d(aa))
+    want = constants.torsions_mask.to(dev)[d(aa)].bool() & known[..., None]
+    assert (rt_mask == want).all()
+    back = torch.remainder(d(ang) + torch.tensor([math.pi, 0, 0, 0, 0], device=dev), 2 * math.pi)
+    well = (torch.sin(d(ang)).abs() > 0.05) & want
+    e_rt, e_rt_all = circ_err(rt[well], back[well]), circ_err(rt[want], back[want])
+    o_tor, o_mask = orc.torsion_angles(T, k_pos.cpu(), aa)
+    e_tor = circ_err(rt.cpu()[well.cpu()], o_tor[well.cpu()])
+    print("torsion angles: round trip %.2e (well conditioned) %.2e (all, acos clamp); vs oracle %.2e" % (e_rt, e_rt_all, e_tor))
+    assert e_rt < 1e-4 and e_rt_all < 2e-3 and e_tor < 1e-4 and (rt_mask.cpu() == o_mask).all()
     # edges: empty input, PAD rows
     assert ops.full_atom_reconstruction(d(Rb[:0]), d(tb[:0]), d(ang[:0]), d(aa[:0]), constants.rigid_tables(dev))[0].shape == (0, L, 14, 3)
     bad = aa.clone()
