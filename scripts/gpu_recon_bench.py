@@ -58,12 +58,16 @@ def main():
         ms_pos = timed(lambda: ops.full_atom_reconstruction(R, t, ang, aa, T, want_frames=False, want_mask=True))
         ms_all = timed(lambda: ops.full_atom_reconstruction(R, t, ang, aa, T, want_frames=True, want_mask=False))
         ms_bb = timed(lambda: ops.reconstruct_backbone(R, t, aa, chain_nb, res_nb, mask, T))
+        pos14 = ops.full_atom_reconstruction(R, t, ang, aa, T, want_frames=False)[0]
+        ms_tor = timed(lambda: ops.torsion_angles(pos14, aa, T))
+        by_tor = n * (42 * 4 + 8 + 5 * 4 + 5)
         by_pos = n * ((9 + 3 + 5) * 4 + 8 + 42 * 4 + 15)          # frames, torsions, types in; pos14 + mask out
         by_all = n * ((9 + 3 + 5) * 4 + 8 + (42 + 54 + 18) * 4)    # + the six frames out
         by_bb = n * ((9 + 3) * 4 + 3 * 8 + 1 + 12 * 4)
         out[tag] = {"residues": n,
                     "pos14+mask": {"ms": ms_pos, "GB/s": by_pos / ms_pos / 1e6, "frac_hbm": by_pos / ms_pos / 1e6 / peak},
                     "pos14+frames": {"ms": ms_all, "GB/s": by_all / ms_all / 1e6, "frac_hbm": by_all / ms_all / 1e6 / peak},
+                    "torsion_angles": {"ms": ms_tor, "GB/s": by_tor / ms_tor / 1e6, "frac_hbm": by_tor / ms_tor / 1e6 / peak},
                     "backbone": {"ms": ms_bb, "GB/s": by_bb / ms_bb / 1e6, "frac_hbm": by_bb / ms_bb / 1e6 / peak}}
     print(json.dumps(out))
 
