@@ -11,10 +11,13 @@
 //
 // All three are O(residues) and HBM bound: 76 B in, 183 - 471 B out per residue.  The first version issued one strided
 // scalar load per thread and element (226 M L1 sectors for 8 M sectors of data: L1TEX 95 % busy, DRAM 23 %); now a CTA
-// takes a tile of 128 consecutive residues, moves its inputs into shared memory with coalesced loads, keeps the
-// per-residue-type constant tables in shared memory, lets one thread compose the frame chain of one residue (products
-// associated exactly as the reference's compose_chain does it: the last two factors first), and then the whole CTA walks
-// the flat output arrays one element per thread, so every HBM store instruction writes consecutive addresses.
+// takes a tile of 128 consecutive residues, moves its inputs into shared memory with flat 16-byte coalesced copies, keeps
+// the per-residue-type constant tables in shared memory, lets one thread compose the frame chain of one residue in
+// registers (products associated exactly as the reference's compose_chain does it: the last two factors first) and drop
+// the atoms of each frame into a staging row as soon as the frame exists, and writes the tile out with flat 16-byte
+// coalesced copies.  (A middle version that parked all six frames in shared memory and computed one output float per
+// thread fixed the sector counts but doubled the instruction count - 400 M warp instructions, 0.67 ms; index
+// arithmetic per output float is what a kernel this light cannot afford.)
 #include "pf_common.cuh"
 #include "pf_geom.cuh"
 
@@ -23,7 +26,6 @@ namespace pf {
 constexpr int RC_T = 128;          // threads = residues per tile
 constexpr int RC_FR = 6;           // frames kept per residue: backbone, psi, chi1..chi4
 constexpr int RC_FW = 12;          // floats per frame: R (9, row-major) | t (3)
-constexpr int RC_ROW = RC_FR * RC_FW + 1;   // +1: residue rows start on distinct banks
 constexpr int RC_NAA = 21;         // rows of the rigid-group tables (20 residue types + UNK)
 
 struct FullAtomArgs {
@@ -51,21 +53,68 @@ __device__ __forceinline__ void torsion_frame(const float* Rp, const float* tp, 
   rigid_apply(Rp, tp, tg, t);
 }
 
+// flat, coalesced global -> shared copy of `count` floats (16-byte vectors when both sides allow it)
+__device__ __forceinline__ void stage_in(float* dst, const float* __restrict__ src, int count, int tid) {
+  if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    const int v = count >> 2;
+    for (int e = tid; e < v; e += RC_T) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(src)[e];
+    for (int e = (v << 2) + tid; e < count; e += RC_T) dst[e] = src[e];
+  } else {
+    for (int e = tid; e < count; e += RC_T) dst[e] = src[e];
+  }
+}
+__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, int count, int tid) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    const int v = count >> 2;
+    for (int e = tid; e < v; e += RC_T) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(src)[e];
+    for (int e = (v << 2) + tid; e < count; e += RC_T) dst[e] = src[e];
+  } else {
+    for (int e = tid; e < count; e += RC_T) dst[e] = src[e];
+  }
+}
+
+constexpr int RC_TROWS = RC_NAA + 1;   // table rows in shared memory: 0..20 residue types, 21 = "no rigid groups"
+
+// The atoms of rigid-group frame f (0 backbone, 1 psi, 2..5 chi1..chi4) of one residue: q = R p + t into the staging row.
+__device__ __forceinline__ void emit_atoms(const uint8_t* ord, const uint8_t* start, const float* apos, int f,
+                                           const float* R, const float* t, float* out_row) {
+  for (int j = start[f]; j < start[f + 1]; ++j) {
+    const int s = ord[j];
+    float q[3];
+    rigid_apply(R, t, apos + s * 3, q);
+    out_row[s * 3] = q[0]; out_row[s * 3 + 1] = q[1]; out_row[s * 3 + 2] = q[2];
+  }
+}
+
 __global__ void __launch_bounds__(RC_T) full_atom_kernel(FullAtomArgs a) {
-  __shared__ float s_fr[RC_T][RC_ROW];              // per residue: six frames; on entry rot | trans | torsions
-  __shared__ float s_grp[RC_NAA * 5 * RC_FW];       // rigid groups 3..7 (psi, chi1..chi4) per type: R | t
-  __shared__ float s_apos[RC_NAA * 14 * 3];
-  __shared__ uint8_t s_agrp[RC_NAA * 14 + 2];
+  __shared__ __align__(16) float s_rot[RC_T * 9];       // staged inputs, flat (odd per-thread strides: no bank conflicts)
+  __shared__ __align__(16) float s_tr[RC_T * 3];
+  __shared__ __align__(16) float s_ang[RC_T * 5];
+  __shared__ __align__(16) float s_out[RC_T * 42];      // staged atom14 rows, flat
+  __shared__ float s_grp[RC_TROWS * 5 * RC_FW];         // rigid groups 3..7 (psi, chi1..chi4) per type: R | t
+  __shared__ float s_apos[RC_TROWS * 14 * 3];
+  __shared__ uint8_t s_ord[RC_TROWS * 14];              // atom slots of a type sorted by frame
+  __shared__ uint8_t s_start[RC_TROWS * 8];             // first entry of frame f in s_ord (7 used)
   __shared__ uint8_t s_mtab[22 * 15 + 2];
   __shared__ int s_aa[RC_T];
   const int tid = threadIdx.x;
-  // ---- constant tables: once per (persistent) CTA
-  for (int e = tid; e < RC_NAA * 5 * RC_FW; e += RC_T) {
+  // ---- constant tables: once per (persistent) CTA; row 21 = zero groups, every atom at the backbone origin
+  for (int e = tid; e < RC_TROWS * 5 * RC_FW; e += RC_T) {
     const int aa = e / (5 * RC_FW), k = e - aa * (5 * RC_FW), g = 3 + k / RC_FW, c = k % RC_FW;
-    s_grp[e] = c < 9 ? a.rigid_rot[(aa * 8 + g) * 9 + c] : a.rigid_trans[(aa * 8 + g) * 3 + (c - 9)];
+    s_grp[e] = aa >= RC_NAA ? 0.f : (c < 9 ? a.rigid_rot[(aa * 8 + g) * 9 + c] : a.rigid_trans[(aa * 8 + g) * 3 + (c - 9)]);
   }
-  for (int e = tid; e < RC_NAA * 14 * 3; e += RC_T) s_apos[e] = a.atom_pos[e];
-  for (int e = tid; e < RC_NAA * 14; e += RC_T) s_agrp[e] = (uint8_t)a.atom_group[e];
+  for (int e = tid; e < RC_TROWS * 14 * 3; e += RC_T) s_apos[e] = e < RC_NAA * 14 * 3 ? a.atom_pos[e] : 0.f;
+  if (tid < RC_TROWS) {
+    int n = 0;
+    for (int f = 0; f < RC_FR; ++f) {
+      s_start[tid * 8 + f] = (uint8_t)n;
+      for (int s = 0; s < 14; ++s) {
+        const int g = tid < RC_NAA ? a.atom_group[tid * 14 + s] : 0;
+        if ((g < 3 ? 0 : g - 2) == f) s_ord[tid * 14 + n++] = (uint8_t)s;   // groups 0..2 carry the backbone frame
+      }
+    }
+    s_start[tid * 8 + RC_FR] = (uint8_t)n;
+  }
   if (a.mask_out)
     for (int e = tid; e < 22 * 15; e += RC_T) s_mtab[e] = a.mask_table[e];
   const long long tiles = (a.n + RC_T - 1) / RC_T;
@@ -73,10 +122,9 @@ __global__ void __launch_bounds__(RC_T) full_atom_kernel(FullAtomArgs a) {
     const long long base = tile * RC_T;
     const int rows = (int)min((long long)RC_T, a.n - base);
     __syncthreads();   // tables visible / previous tile's readers done
-    // ---- inputs, coalesced: rot -> F[0..8], trans -> F[9..11], torsions -> F[12..16] (consumed before frame 1 lands)
-    for (int e = tid; e < rows * 9; e += RC_T) s_fr[e / 9][e % 9] = a.rot[base * 9 + e];
-    for (int e = tid; e < rows * 3; e += RC_T) s_fr[e / 3][9 + e % 3] = a.trans[base * 3 + e];
-    for (int e = tid; e < rows * 5; e += RC_T) s_fr[e / 5][12 + e % 5] = a.angles[base * 5 + e];
+    stage_in(s_rot, a.rot + base * 9, rows * 9, tid);
+    stage_in(s_tr, a.trans + base * 3, rows * 3, tid);
+    stage_in(s_ang, a.angles + base * 5, rows * 5, tid);
     if (tid < rows) {
       const long long aa64 = a.aa[base + tid];
       // 0..20: table rows; 21 (PAD): no rigid groups, zero mask row; anything else: nothing at all
@@ -84,59 +132,52 @@ __global__ void __launch_bounds__(RC_T) full_atom_kernel(FullAtomArgs a) {
     }
     __syncthreads();
     if (tid < rows) {
-      float* F = s_fr[tid];
-      const int aa = s_aa[tid];
-      float ang[5];
+      const int aa = (s_aa[tid] >= 0 && s_aa[tid] < RC_NAA) ? s_aa[tid] : RC_NAA;
+      const uint8_t* ord = s_ord + aa * 14;
+      const uint8_t* start = s_start + aa * 8;
+      const float* apos = s_apos + aa * 42;
+      const float* grp = s_grp + aa * 5 * RC_FW;
+      float* row = s_out + tid * 42;
+      const long long r = base + tid;
+      float R0[9], t0[3];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) ang[k] = F[12 + k];
-      // rigid groups: 3 psi, 4..7 chi1..chi4; parents: psi and chi1 hang off the backbone, chi_k off chi_{k-1}
+      for (int k = 0; k < 9; ++k) R0[k] = s_rot[tid * 9 + k];
 #pragma unroll
-      for (int f = 1; f < RC_FR; ++f) {
-        const int parent = (f <= 2) ? 0 : f - 1;
-        float Rg[9], tg[3], Rp[9], tp[3];
-        if (aa >= 0 && aa < RC_NAA) {
-          const float* G = s_grp + (aa * 5 + (f - 1)) * RC_FW;
+      for (int k = 0; k < 3; ++k) t0[k] = s_tr[tid * 3 + k];
+      auto put_frame = [&](int f, const float* R, const float* t) {
+        if (a.R_ret) {
 #pragma unroll
-          for (int k = 0; k < 9; ++k) Rg[k] = G[k];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) tg[k] = G[9 + k];
-        } else {
-#pragma unroll
-          for (int k = 0; k < 9; ++k) Rg[k] = 0.f;
-          tg[0] = tg[1] = tg[2] = 0.f;
+          for (int k = 0; k < 9; ++k) a.R_ret[(r * RC_FR + f) * 9 + k] = R[k];
         }
+        if (a.t_ret) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) Rp[k] = F[parent * RC_FW + k];
+          for (int k = 0; k < 3; ++k) a.t_ret[(r * RC_FR + f) * 3 + k] = t[k];
+        }
+      };
+      emit_atoms(ord, start, apos, 0, R0, t0, row);
+      put_frame(0, R0, t0);
+      float Rc[9], tc[3];
+      // psi (group 3) and chi1 (group 4) hang off the backbone frame, chi_k off chi_{k-1}
+      torsion_frame(R0, t0, grp, grp + 9, s_ang[tid * 5], Rc, tc);
+      emit_atoms(ord, start, apos, 1, Rc, tc, row);
+      put_frame(1, Rc, tc);
+      torsion_frame(R0, t0, grp + RC_FW, grp + RC_FW + 9, s_ang[tid * 5 + 1], Rc, tc);
+      emit_atoms(ord, start, apos, 2, Rc, tc, row);
+      put_frame(2, Rc, tc);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) tp[k] = F[parent * RC_FW + 9 + k];
-        torsion_frame(Rp, tp, Rg, tg, ang[f - 1], F + f * RC_FW, F + f * RC_FW + 9);
+      for (int f = 3; f < RC_FR; ++f) {
+        float Rn[9], tn[3];
+        torsion_frame(Rc, tc, grp + (f - 1) * RC_FW, grp + (f - 1) * RC_FW + 9, s_ang[tid * 5 + f - 1], Rn, tn);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rc[k] = Rn[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tc[k] = tn[k];
+        emit_atoms(ord, start, apos, f, Rc, tc, row);
+        put_frame(f, Rc, tc);
       }
     }
     __syncthreads();
-    // ---- atom14 coordinates: one output float per thread and trip (residue r, slot s, axis k)
-    for (int e = tid; e < rows * 42; e += RC_T) {
-      const int r = e / 42, c = e - r * 42, s = c / 3, k = c - s * 3, aa = s_aa[r];
-      float px = 0.f, py = 0.f, pz = 0.f;
-      int f = 0;
-      if (aa >= 0 && aa < RC_NAA) {
-        const int g = s_agrp[aa * 14 + s];
-        f = g < 3 ? 0 : g - 2;   // backbone / omega / phi groups all carry the backbone frame (torsion.py:214-215)
-        const float* P = s_apos + (aa * 14 + s) * 3;
-        px = P[0]; py = P[1]; pz = P[2];
-      }
-      const float* Fr = s_fr[r] + f * RC_FW;
-      a.pos14[base * 42 + e] = fmaf(Fr[k * 3 + 2], pz, fmaf(Fr[k * 3 + 1], py, Fr[k * 3] * px)) + Fr[9 + k];
-    }
-    if (a.R_ret)
-      for (int e = tid; e < rows * RC_FR * 9; e += RC_T) {
-        const int r = e / (RC_FR * 9), k = e - r * (RC_FR * 9);
-        a.R_ret[base * (RC_FR * 9) + e] = s_fr[r][(k / 9) * RC_FW + k % 9];
-      }
-    if (a.t_ret)
-      for (int e = tid; e < rows * RC_FR * 3; e += RC_T) {
-        const int r = e / (RC_FR * 3), k = e - r * (RC_FR * 3);
-        a.t_ret[base * (RC_FR * 3) + e] = s_fr[r][(k / 3) * RC_FW + 9 + k % 3];
-      }
+    stage_out(a.pos14 + base * 42, s_out, rows * 42, tid);
     if (a.mask_out) {
       // four mask bytes per thread and store; base * 15 is a multiple of 4 (base is a multiple of 128)
       const int words = (rows * 15 + 3) / 4;
@@ -169,30 +210,32 @@ struct BackboneArgs {
 };
 
 __global__ void __launch_bounds__(RC_T) backbone_kernel(BackboneArgs a) {
-  __shared__ float s_in[RC_T + 1][13];     // rot | trans of the tile's residues and the one after it
-  __shared__ float s_out[RC_T][13];
-  __shared__ float s_tab[RC_NAA * 12];     // N, CA, C (backbone frame) | O (psi frame) per residue type
+  __shared__ __align__(16) float s_rot[(RC_T + 1) * 9 + 3];   // the tile's residues and the one after it
+  __shared__ __align__(16) float s_tr[(RC_T + 1) * 3 + 1];
+  __shared__ __align__(16) float s_out[RC_T * 12];
+  __shared__ float s_bb[RC_NAA * 9];                          // N, CA, C in the backbone frame per residue type
+  __shared__ float s_ox[RC_NAA * 3];                          // O in the psi frame
   const int tid = threadIdx.x;
   const long long n = (long long)a.N * a.L;
   const long long base = (long long)blockIdx.x * RC_T;
   const int rows = (int)min((long long)RC_T, n - base);
   const int rows_in = (int)min((long long)RC_T + 1, n - base);
-  for (int e = tid; e < RC_NAA * 12; e += RC_T) {
-    const int aa = e / 12, c = e - aa * 12;
-    s_tab[e] = c < 9 ? a.bb_coords[aa * 9 + c] : a.bb_oxygen[aa * 3 + (c - 9)];
-  }
-  for (int e = tid; e < rows_in * 9; e += RC_T) s_in[e / 9][e % 9] = a.rot[base * 9 + e];
-  for (int e = tid; e < rows_in * 3; e += RC_T) s_in[e / 3][9 + e % 3] = a.trans[base * 3 + e];
+  for (int e = tid; e < RC_NAA * 9; e += RC_T) s_bb[e] = a.bb_coords[e];
+  if (tid < RC_NAA * 3) s_ox[tid] = a.bb_oxygen[tid];
+  stage_in(s_rot, a.rot + base * 9, rows_in * 9, tid);
+  stage_in(s_tr, a.trans + base * 3, rows_in * 3, tid);
   __syncthreads();
   if (tid < rows) {
     const long long r = base + tid;
     const int l = (int)(r % a.L);
-    const float* R = s_in[tid];
-    const float* t = R + 9;
-    const int aa = clamp_aa(a.aa[r]);                                     // geometry.py:462
-    float bb[9];
+    float R[9], t[3], bb[9];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) rigid_apply(R, t, s_tab + aa * 12 + k * 3, bb + k * 3);
+    for (int k = 0; k < 9; ++k) R[k] = s_rot[tid * 9 + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = s_tr[tid * 3 + k];
+    const int aa = clamp_aa(a.aa[r]);                                     // geometry.py:462
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rigid_apply(R, t, s_bb + aa * 9 + k * 3, bb + k * 3);
     // psi_i = dihedral(N_i, CA_i, C_i, N_{i+1}) when i+1 continues the chain (geometry.py:355-390, topology.py:5-24)
     float psi = 0.f;
     if (l + 1 < a.L) {
@@ -201,7 +244,7 @@ __global__ void __launch_bounds__(RC_T) backbone_kernel(BackboneArgs a) {
       if (d == 1 && a.chain_nb[r + 1] == a.chain_nb[r] && a.mask[r]) {
         const int aa1 = clamp_aa(a.aa[r + 1]);
         float n1[3];
-        rigid_apply(s_in[tid + 1], s_in[tid + 1] + 9, s_tab + aa1 * 12, n1);
+        rigid_apply(s_rot + (tid + 1) * 9, s_tr + (tid + 1) * 3, s_bb + aa1 * 9, n1);
         psi = dihedral4(bb, bb + 3, bb + 6, n1);
       }
     }
@@ -216,14 +259,14 @@ __global__ void __launch_bounds__(RC_T) backbone_kernel(BackboneArgs a) {
       M[i * 3 + 2] = fmaf(R[i * 3 + 2], c, -(R[i * 3 + 1] * s));
     }
     float o[3];
-    rigid_apply(M, t, s_tab + aa * 12 + 9, o);
+    rigid_apply(M, t, s_ox + aa * 3, o);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) s_out[tid][k] = bb[k];
+    for (int k = 0; k < 9; ++k) s_out[tid * 12 + k] = bb[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) s_out[tid][9 + k] = o[k];
+    for (int k = 0; k < 3; ++k) s_out[tid * 12 + 9 + k] = o[k];
   }
   __syncthreads();
-  for (int e = tid; e < rows * 12; e += RC_T) a.pos_bb[base * 12 + e] = s_out[e / 12][e % 12];
+  stage_out(a.pos_bb + base * 12, s_out, rows * 12, tid);
 }
 
 // ---- torsions from coordinates -------------------------------------------------------------------------------------
@@ -235,20 +278,20 @@ struct TorsionArgs {
 };
 
 __global__ void __launch_bounds__(RC_T) torsion_angles_kernel(TorsionArgs a) {
-  __shared__ float s_pos[RC_T][TA_MAXA * 3 + 1];
+  __shared__ __align__(16) float s_pos[RC_T * TA_MAXA * 3];
   __shared__ int8_t s_chi[RC_NAA * 16];
-  __shared__ float s_val[RC_T * 5];
+  __shared__ __align__(16) float s_val[RC_T * 5];
   __shared__ uint8_t s_msk[RC_T * 5];
   const int tid = threadIdx.x;
   const long long base = (long long)blockIdx.x * RC_T;
   const int rows = (int)min((long long)RC_T, a.n - base);
   const int W = a.A * 3;
   for (int e = tid; e < RC_NAA * 16; e += RC_T) s_chi[e] = (int8_t)a.chi_atoms[e];
-  for (int e = tid; e < rows * W; e += RC_T) s_pos[e / W][e % W] = a.pos[base * W + e];
+  stage_in(s_pos, a.pos + base * W, rows * W, tid);
   __syncthreads();
   if (tid < rows) {
     const long long aa64 = a.aa[base + tid];
-    const float* P = s_pos[tid];
+    const float* P = s_pos + tid * W;
     float v[5];
     bool ok[5];
     if (aa64 >= 0 && aa64 < 20) {                                   // torsion.py:52: 0..19 only
@@ -272,10 +315,8 @@ __global__ void __launch_bounds__(RC_T) torsion_angles_kernel(TorsionArgs a) {
     for (int i = 0; i < 5; ++i) { s_val[tid * 5 + i] = v[i]; s_msk[tid * 5 + i] = ok[i] ? 1 : 0; }
   }
   __syncthreads();
-  for (int e = tid; e < rows * 5; e += RC_T) {
-    a.torsion[base * 5 + e] = s_val[e];
-    a.mask[base * 5 + e] = s_msk[e];
-  }
+  stage_out(a.torsion + base * 5, s_val, rows * 5, tid);
+  for (int e = tid; e < rows * 5; e += RC_T) a.mask[base * 5 + e] = s_msk[e];
 }
 
 }  // namespace pf
@@ -294,9 +335,9 @@ extern "C" int pf_full_atom_reconstruction(const float* rot, const float* trans,
   PF_REQUIRE(!mask_out || (reinterpret_cast<uintptr_t>(mask_out) & 3u) == 0, PF_ERR_MISALIGNED);
   FullAtomArgs a{rot, trans, angles, aa, rigid_rot, rigid_trans, atom_group, atom_pos, heavyatom_mask_table,
                  pos14, R_ret, t_ret, mask_out, n};
-  // persistent CTAs (4 fit on an SM next to their 46 KB of shared memory): the constant tables are staged once per CTA
+  // persistent CTAs (5 fit on an SM next to their 41 KB of shared memory): the constant tables are staged once per CTA
   const long long tiles = (n + RC_T - 1) / RC_T;
-  const unsigned grid = (unsigned)min(tiles, (long long)num_sms() * 4);
+  const unsigned grid = (unsigned)min(tiles, (long long)num_sms() * 5);
   full_atom_kernel<<<grid, RC_T, 0, as_stream(stream)>>>(a);
   PF_CHECK_LAUNCH();
   return PF_OK;
