@@ -86,7 +86,14 @@ __device__ __forceinline__ void emit_atoms(const uint8_t* ord, const uint8_t* st
   }
 }
 
+// FRAMES: the six frames of every residue are also wanted (R_ret / t_ret): they are staged in 36 KB of dynamic shared
+// memory ([r][f][9] and [r][f][3], flat) and leave as coalesced copies like the atoms.  (Storing them straight from
+// registers - 72 scalar stores per thread at a 216-byte stride - took 1.7 ms against 0.41 ms without frames.)
+template <bool FRAMES>
 __global__ void __launch_bounds__(RC_T) full_atom_kernel(FullAtomArgs a) {
+  extern __shared__ __align__(16) float s_dyn[];
+  float* const s_R = s_dyn;                             // FRAMES only: [RC_T][6][9]
+  float* const s_t = s_dyn + RC_T * RC_FR * 9;          //              [RC_T][6][3]
   __shared__ __align__(16) float s_rot[RC_T * 9];       // staged inputs, flat (odd per-thread strides: no bank conflicts)
   __shared__ __align__(16) float s_tr[RC_T * 3];
   __shared__ __align__(16) float s_ang[RC_T * 5];
@@ -138,20 +145,17 @@ __global__ void __launch_bounds__(RC_T) full_atom_kernel(FullAtomArgs a) {
       const float* apos = s_apos + aa * 42;
       const float* grp = s_grp + aa * 5 * RC_FW;
       float* row = s_out + tid * 42;
-      const long long r = base + tid;
       float R0[9], t0[3];
 #pragma unroll
       for (int k = 0; k < 9; ++k) R0[k] = s_rot[tid * 9 + k];
 #pragma unroll
       for (int k = 0; k < 3; ++k) t0[k] = s_tr[tid * 3 + k];
       auto put_frame = [&](int f, const float* R, const float* t) {
-        if (a.R_ret) {
+        if (FRAMES) {
 #pragma unroll
-          for (int k = 0; k < 9; ++k) a.R_ret[(r * RC_FR + f) * 9 + k] = R[k];
-        }
-        if (a.t_ret) {
+          for (int k = 0; k < 9; ++k) s_R[(tid * RC_FR + f) * 9 + k] = R[k];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) a.t_ret[(r * RC_FR + f) * 3 + k] = t[k];
+          for (int k = 0; k < 3; ++k) s_t[(tid * RC_FR + f) * 3 + k] = t[k];
         }
       };
       emit_atoms(ord, start, apos, 0, R0, t0, row);
@@ -178,6 +182,10 @@ __global__ void __launch_bounds__(RC_T) full_atom_kernel(FullAtomArgs a) {
     }
     __syncthreads();
     stage_out(a.pos14 + base * 42, s_out, rows * 42, tid);
+    if (FRAMES) {
+      if (a.R_ret) stage_out(a.R_ret + base * (RC_FR * 9), s_R, rows * RC_FR * 9, tid);
+      if (a.t_ret) stage_out(a.t_ret + base * (RC_FR * 3), s_t, rows * RC_FR * 3, tid);
+    }
     if (a.mask_out) {
       // four mask bytes per thread and store; base * 15 is a multiple of 4 (base is a multiple of 128)
       const int words = (rows * 15 + 3) / 4;
@@ -335,10 +343,19 @@ extern "C" int pf_full_atom_reconstruction(const float* rot, const float* trans,
   PF_REQUIRE(!mask_out || (reinterpret_cast<uintptr_t>(mask_out) & 3u) == 0, PF_ERR_MISALIGNED);
   FullAtomArgs a{rot, trans, angles, aa, rigid_rot, rigid_trans, atom_group, atom_pos, heavyatom_mask_table,
                  pos14, R_ret, t_ret, mask_out, n};
-  // persistent CTAs (5 fit on an SM next to their 41 KB of shared memory): the constant tables are staged once per CTA
+  // persistent CTAs (5 fit on an SM next to their 41 KB of shared memory, 2 with the frame staging): the constant
+  // tables are staged once per CTA
   const long long tiles = (n + RC_T - 1) / RC_T;
-  const unsigned grid = (unsigned)min(tiles, (long long)num_sms() * 5);
-  full_atom_kernel<<<grid, RC_T, 0, as_stream(stream)>>>(a);
+  if (R_ret || t_ret) {
+    const int dyn = RC_T * RC_FR * RC_FW * (int)sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(full_atom_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const unsigned grid = (unsigned)min(tiles, (long long)num_sms() * 2);
+    full_atom_kernel<true><<<grid, RC_T, dyn, as_stream(stream)>>>(a);
+  } else {
+    const unsigned grid = (unsigned)min(tiles, (long long)num_sms() * 5);
+    full_atom_kernel<false><<<grid, RC_T, 0, as_stream(stream)>>>(a);
+  }
   PF_CHECK_LAUNCH();
   return PF_OK;
 }
