@@ -684,3 +684,35 @@ def test_training_forward_losses_and_backward(dev, model):
         msg.append("%s %.1e/%.1e" % (k, ek, ea))
         assert ek < TOL and ea < TOL, (k, float(kern[k]), float(auto[k]), float(g[k]))
     print("training losses vs reference (kernels / autograd): " + ", ".join(msg) + "; params with grad %d of %d" % (n_with, len(grads)))
+
+
+def test_sample_to_pdb_pipeline(dev, model, tmp_path):
+    """FlowModel.sample -> save_samples_sc / save_samples_bb (models_con/inference.py:105-106, sample.py:68-120) on the
+    device: the atoms written for the generated residues are the oracle's reconstruction of the sampled frames /
+    torsions / types (PDB precision, 1e-3 A), the context residues are the batch's own atoms."""
+    from pepflowww_b200 import constants, sample, writers
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    from pepflowww_b200.utils import recursive_to
+    batch = recursive_to(synthetic_batch(2, 14, 5, seed=9), dev)
+    with torch.no_grad():
+        traj = model.sample(batch, num_steps=2)
+    samples = dict(traj[-1])
+    samples["batch"] = batch
+    T = constants.rigid_tables("cpu")
+    want, _, _ = orc.full_atom_reconstruction(T, samples["rotmats"], samples["trans"], samples["angles"], samples["seqs"])
+    gen = batch["generate_mask"].cpu()
+    for fn in (sample.save_samples_sc, sample.save_samples_bb):
+        paths = fn(samples, str(tmp_path / fn.__name__))
+        assert len(paths) == 3
+        atoms = writers.parse_pdb_atoms(open(paths[0]).read())
+        pep = [a for a in atoms if a[3] == "A"]
+        names = {"N": 0, "CA": 1, "C": 2}
+        checked = 0
+        for _, name, _, _, resseq, xyz in pep:
+            if name in names:                      # backbone atoms do not depend on psi: same in both writers
+                r = int(gen[0].nonzero()[resseq - 1])
+                assert max(abs(x - float(y)) for x, y in zip(xyz, want[0, r, names[name]])) < 2e-3
+                checked += 1
+        assert checked == 3 * int(gen[0].sum())
+        gt = writers.parse_pdb_atoms(open(paths[-1]).read())
+        assert [a[1:] for a in atoms if a[3] == "B"] == [a[1:] for a in gt if a[3] == "B"]

@@ -188,3 +188,42 @@ def test_autograd_denoiser_matches_reference_and_reaches_every_parameter(state_d
     assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
     with torch.enable_grad(), pytest.raises(RuntimeError):     # the kernel path refuses to run under autograd
         m.ga_encoder(*[g[k] for k in keys])
+
+
+def test_save_samples_pipeline_on_host(tmp_path, monkeypatch):
+    """sample.save_samples_sc / _bb (models_con/sample.py:68-120): file set, chain split, context residues untouched,
+    generated residues replaced - with the device geometry substituted by the oracle so the host logic runs on CPU."""
+    from pepflowww_b200 import constants, sample, writers
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    batch = synthetic_batch(3, 10, 4, seed=2)
+    T = constants.rigid_tables("cpu")
+    B, L = batch["aa"].shape
+    g = torch.Generator().manual_seed(1)
+    q = torch.nn.functional.normalize(torch.randn(B, L, 4, generator=g), dim=-1)
+    samples = {"rotmats": orc.quat_to_rot(q), "trans": torch.randn(B, L, 3, generator=g) * 5,
+               "angles": torch.rand(B, L, 5, generator=g) * 6.28, "seqs": torch.randint(0, 20, (B, L), generator=g),
+               "batch": batch}
+    samples["seqs"] = torch.where(batch["generate_mask"], samples["seqs"], batch["aa"])
+
+    def side(s):
+        pos14, _, _ = orc.full_atom_reconstruction(T, s["rotmats"], s["trans"], s["angles"], s["seqs"])
+        return torch.nn.functional.pad(pos14, (0, 0, 0, 1)), constants.restype_to_heavyatom_masks[s["seqs"]]
+
+    monkeypatch.setattr(sample, "_device_of", lambda s: torch.device("cpu"))
+    monkeypatch.setattr(sample.torsion, "reconstruct_side_chains", side)
+    monkeypatch.setattr(sample.geometry, "reconstruct_backbone",
+                        lambda R, t, aa, c, r, m: orc.reconstruct_backbone(T, R, t, aa, c, r, m))
+    for fn, n_gen_atoms in ((sample.save_samples_sc, None), (sample.save_samples_bb, 4)):
+        paths = fn(samples, str(tmp_path / fn.__name__))
+        assert [p.split("/")[-1] for p in paths] == ["sample_0.pdb", "sample_1.pdb", "sample_2.pdb", "gt.pdb"]
+        atoms = writers.parse_pdb_atoms(open(paths[0]).read())      # gt.pdb is complex 0 (replicas in the reference)
+        gt = writers.parse_pdb_atoms(open(paths[-1]).read())
+        assert {a[3] for a in atoms} == {"A", "B"}
+        ctx = lambda rows: [a[1:] for a in rows if a[3] == "B"]
+        assert ctx(atoms) == ctx(gt)                                  # pocket (context) residues: written unchanged
+        pep = [a for a in atoms if a[3] == "A"]
+        assert len({a[4] for a in pep}) == 4
+        if n_gen_atoms:
+            assert len(pep) == 4 * n_gen_atoms and {a[1] for a in pep} == {"N", "CA", "C", "O"}
+        else:
+            assert len(pep) == int(constants.restype_to_heavyatom_masks[samples["seqs"][0][batch["generate_mask"][0]]].sum())
