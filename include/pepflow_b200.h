@@ -40,7 +40,7 @@ typedef enum pf_status {
 } pf_status;
 
 /* ---- library ---------------------------------------------------------------------------- */
-int pf_version(void);                       /* ABI version (this header: 2)                   */
+int pf_version(void);                       /* ABI version (this header: 3; 3 added the post-sampling entry points) */
 const char* pf_strerror(int status);
 int pf_init(int device);                    /* opt kernels into >48 KB shared memory, query SMs */
 int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_points, int no_v_points,

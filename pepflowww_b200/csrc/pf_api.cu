@@ -151,7 +151,7 @@ static size_t enumerate_packables(const pf_ga_weights* w, std::vector<PackItem>*
 
 extern "C" {
 
-int pf_version(void) { return 2; }
+int pf_version(void) { return 3; }
 
 size_t pf_ga_prepack_bytes(const pf_ga_weights* w) {
   if (!w || w->num_blocks < 1 || w->num_blocks > PF_MAX_BLOCKS) return 0;
