@@ -227,3 +227,19 @@ def test_save_samples_pipeline_on_host(tmp_path, monkeypatch):
             assert len(pep) == 4 * n_gen_atoms and {a[1] for a in pep} == {"N", "CA", "C", "O"}
         else:
             assert len(pep) == int(constants.restype_to_heavyatom_masks[samples["seqs"][0][batch["generate_mask"][0]]].sum())
+
+
+def test_inference_metrics_arithmetic():
+    """sample_metrics (models_con/inference.py:76-78): RMSDs and recovery are taken over generated residues only."""
+    from pepflowww_b200.inference import sample_metrics
+    B, L = 2, 6
+    gm = torch.zeros(B, L, dtype=torch.bool)
+    gm[:, 4:] = True
+    eye = torch.eye(3).expand(B, L, 3, 3)
+    final = {"trans": torch.zeros(B, L, 3), "trans_1": torch.zeros(B, L, 3), "rotmats": eye.clone(), "rotmats_1": eye.clone(),
+             "seqs": torch.zeros(B, L, dtype=torch.long), "seqs_1": torch.zeros(B, L, dtype=torch.long)}
+    final["trans"][:, :4] += 100.0          # context residues never count
+    final["trans"][:, 4:, 0] = 3.0
+    final["seqs"][0, 5] = 7
+    m = sample_metrics(final, {"generate_mask": gm})
+    assert abs(m["tran"] - 3.0) < 1e-5 and m["rot"] == 0.0 and abs(m["aar"] - 0.75) < 1e-6 and m["len"] == 4
