@@ -61,6 +61,25 @@ def train_step(model, batch, optimizer, loss_weights, max_grad_norm):
     return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}, grad_norm
 
 
+def inf_iterator(iterable):
+    """Endless pass over a DataLoader (pepflow/utils/misc.py inf_iterator, used at train_ddp.py:91)."""
+    while True:
+        for x in iterable:
+            yield x
+
+
+def make_loader(dataset, batch_size, rank=0, world=1, num_workers=0, seed=0):
+    """DistributedSampler(shuffle=True) + DataLoader(PaddingCollate()) as train_ddp.py:88-91: every rank draws a
+    disjoint shard of each epoch's permutation."""
+    from torch.utils.data import DataLoader
+    from torch.utils.data.distributed import DistributedSampler
+
+    from .pep_dataloader import PaddingCollate
+    sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=True, seed=seed)
+    return DataLoader(dataset, batch_size=batch_size, collate_fn=PaddingCollate(), sampler=sampler,
+                      num_workers=num_workers, pin_memory=torch.cuda.is_available())
+
+
 def checkpoint_dict(config, model, optimizer, scheduler, iteration):
     return {"config": config, "model": model.state_dict(), "optimizer": optimizer.state_dict(),
             "scheduler": scheduler.state_dict(), "iteration": iteration}
@@ -69,7 +88,7 @@ def checkpoint_dict(config, model, optimizer, scheduler, iteration):
 def main(argv=None):
     from .config import load_config
     from .flow_model import FlowModel
-    from .pep_dataloader import synthetic_batch
+    from .pep_dataloader import SyntheticPepDataset
     from .utils import recursive_to, seed_all
 
     ap = argparse.ArgumentParser()
@@ -80,6 +99,8 @@ def main(argv=None):
     ap.add_argument("--pocket", type=int, default=48)
     ap.add_argument("--peptide", type=int, default=12)
     ap.add_argument("--save", default=None)
+    ap.add_argument("--resume", default=None)
+    ap.add_argument("--dataset-size", type=int, default=4096, help="synthetic complexes per epoch")
     args = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -96,15 +117,24 @@ def main(argv=None):
     optimizer = get_optimizer(config.train.optimizer, model)
     scheduler = get_scheduler(config.train.scheduler, optimizer)
     bs = args.batch_size or config.train.batch_size
+    it_first = 1
+    if args.resume:                                     # train_ddp.py:105-114
+        ckpt = torch.load(args.resume, map_location=dev, weights_only=False)
+        it_first = ckpt["iteration"]
+        net.load_state_dict(ckpt["model"])
+        optimizer.load_state_dict(ckpt["optimizer"])
+        scheduler.load_state_dict(ckpt["scheduler"])
+    dataset = SyntheticPepDataset(args.dataset_size, args.pocket, args.peptide, seed=0)
+    train_iterator = inf_iterator(make_loader(dataset, bs, rank, world, seed=config.train.seed))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     last = None
-    for it in range(1, args.warmup + args.iters + 1):
-        if it == args.warmup + 1:
+    for it in range(it_first, it_first + args.warmup + args.iters):
+        if it == it_first + args.warmup:
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             ev0.record()
-        batch = recursive_to(synthetic_batch(bs, args.pocket, args.peptide, seed=1000 * rank + it, eight=True), dev)
+        batch = recursive_to(next(train_iterator), dev)
         last = train_step(model, batch, optimizer, config.train.loss_weights, config.train.max_grad_norm)
     ev1.record()
     torch.cuda.synchronize()
@@ -114,7 +144,7 @@ def main(argv=None):
     if rank == 0:
         if args.save:
             torch.save(checkpoint_dict(config, model.module if world > 1 else model, optimizer, scheduler,
-                                       args.warmup + args.iters), args.save)
+                                       it_first + args.warmup + args.iters), args.save)
         print(json.dumps({"metric": "training samples/sec (flow-matching loss, fwd+bwd+Adam)", "unit": "samples/s",
                           "value": bs * world / (float(ms) / 1e3), "ms_per_iter": float(ms), "n_gpus": world,
                           "batch_per_gpu": bs, "residues": args.pocket + args.peptide, "loss": float(last[0]),

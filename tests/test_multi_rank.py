@@ -126,7 +126,13 @@ def _ddp_worker(rank, world, port, out):
         net.zero_grad()
         loss, parts, gnorm = train.train_step(ddp, _ddp_inputs(7 + rank), opt, weights, net.cfg.train.max_grad_norm)
         digest = float(sum(p.double().sum() for p in net.parameters()))
-        out.put((rank, err, digest, float(loss), sorted(parts), int(got.numel())))
+        # the loader of the harness: disjoint shards of one epoch, collated to the PaddingCollate schema
+        from pepflowww_b200.pep_dataloader import SyntheticPepDataset
+        loader = train.make_loader(SyntheticPepDataset(8, 6, 3, seed=0), 2, rank, world, seed=114514)
+        ids = [i for b in loader for i in b["id"]]
+        first = next(train.inf_iterator(loader))
+        assert first["aa"].shape == (2, 16) and first["res_mask"].sum() == 18          # 9 residues padded to 16
+        out.put((rank, err, digest, float(loss), sorted(parts), int(got.numel()), ids))
     finally:
         dist.destroy_process_group()
 
@@ -148,3 +154,4 @@ def test_ddp_gradient_allreduce_on_the_denoiser():
     assert res[0][2] == res[1][2]                              # identical parameters after the step
     assert res[0][4] == ["angle_loss", "bb_atom_loss", "rot_loss", "seqs_loss", "torsion_loss", "trans_loss"]
     assert res[0][5] > 6_000_000                               # the ga_encoder's parameters all took part
+    assert len(res[0][6]) == 4 and not set(res[0][6]) & set(res[1][6]) and len(set(res[0][6]) | set(res[1][6])) == 8
