@@ -4,7 +4,7 @@
  *
  * The reference (Ced3-han/PepFlowww) has no FFI / operator registry: its boundary is the Python
  * object API (FlowModel.forward/.sample, GAEncoder.forward, ...).  The host side of this repo
- * (pepflowww_b200/*.py) keeps that object API and binds the entry points below with ctypes; each
+ * (the modules of pepflowww_b200/) keeps that object API and binds the entry points below with ctypes; each
  * entry point names the reference interface it replaces (paths relative to the reference root).
  *
  * Conventions (all entry points):

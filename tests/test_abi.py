@@ -80,3 +80,21 @@ def test_no_cpu_fallback():
         ops.linear(torch.zeros(4, 8), torch.zeros(8, 8))
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.so3_log(torch.eye(3)[None])
+
+
+def test_plain_c_consumer(tmp_path):
+    """include/pepflow_b200.h compiles as C99 with -Wall -Werror and a dlopen consumer (tests/c/abi_smoke.c) reaches the
+    entry points with plain pointers and sizes - the binding surface a cgo / JNI / ctypes stub sees.  No GPU needed."""
+    import shutil
+    import subprocess
+    from pepflowww_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c", "abi_smoke.c"), "-ldl", "-o", exe], check=True)
+    r = subprocess.run([exe, _lib.LIB_PATH], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "abi ok" in r.stdout
