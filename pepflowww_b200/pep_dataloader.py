@@ -82,8 +82,9 @@ DEFAULT_PAD_VALUES = {"aa": PAD_RESIDUE_INDEX, "chain_id": " ", "icode": " "}
 
 
 class PaddingCollate:
-    def __init__(self, length_ref_key="aa", pad_values=DEFAULT_PAD_VALUES, eight=True):
+    def __init__(self, length_ref_key="aa", pad_values=DEFAULT_PAD_VALUES, no_padding=(), eight=True):
         self.length_ref_key, self.pad_values, self.eight = length_ref_key, pad_values, eight
+        self.no_padding = set(no_padding)
 
     def _pad(self, key, x, n):
         value = self.pad_values.get(key, 0)
@@ -105,7 +106,7 @@ class PaddingCollate:
             keys &= set(d.keys())
         padded = []
         for d in data_list:
-            item = {k: self._pad(k, v, n) for k, v in d.items() if k in keys}
+            item = {k: (v if k in self.no_padding else self._pad(k, v, n)) for k, v in d.items() if k in keys}
             l = d[self.length_ref_key].size(0)
             item["res_mask"] = torch.cat([torch.ones(l, dtype=torch.bool), torch.zeros(n - l, dtype=torch.bool)])
             padded.append(item)

@@ -243,3 +243,25 @@ def test_inference_metrics_arithmetic():
     final["seqs"][0, 5] = 7
     m = sample_metrics(final, {"generate_mask": gm})
     assert abs(m["tran"] - 3.0) < 1e-5 and m["rot"] == 0.0 and abs(m["aar"] - 0.75) < 1e-6 and m["len"] == 4
+
+
+def test_padding_collate_matches_reference():
+    """PaddingCollate (pepflow/utils/data.py:19-78) against the reference's output on ragged items with list / string
+    fields: same keys (common keys only), same padding values (aa -> 21, chain_id / icode -> ' ', others 0), same
+    res_mask, same transposed list-of-tuples layout for the string lists, with and without the multiple-of-8 rounding."""
+    import json
+    from tests.golden.make_golden_collate import items
+    from pepflowww_b200.pep_dataloader import PaddingCollate
+    g = load_golden("collate")
+    for tag, eight in (("e8", True), ("e1", False)):
+        b = PaddingCollate(eight=eight)(items())
+        want = {k[len(tag) + 1:]: v for k, v in g.items() if k.startswith(tag + "_")}
+        assert {k.replace("__json", "") for k in want} == set(b), (sorted(want), sorted(b))
+        for k, v in want.items():
+            if k.endswith("__json"):
+                ref = json.loads(bytes(v.numpy().tolist()).decode())
+                ours = json.loads(json.dumps(b[k[:-6]]))
+                assert ours == ref, k
+            else:
+                assert b[k].dtype == v.dtype and torch.equal(b[k], v), k
+    assert PaddingCollate(no_padding={"resseq"}).no_padding == {"resseq"}
