@@ -4,6 +4,7 @@ complexes (BASELINE.json metric), with the fused-IPA HBM roofline and the refere
 
     python bench.py --gpus N --steps K --warmup W            # our sm_100a path (torchrun for N > 1)
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+    python bench.py --config cfg2|cfg1|cfg3                  # the other BASELINE.json shapes (cfg4 is the default)
 
 A "step" is ONE Euler iteration of FlowModel.sample over the whole per-GPU batch (denoiser evaluation
 = GAEncoder.forward, post-processing, manifold Euler update: flow_model.py:287-343), i.e. one pass of the
@@ -27,6 +28,8 @@ import torch  # noqa: E402
 EULER_STEPS = 200
 METRIC = "sampled peptides/sec @ 200 Euler steps, 256-res pocket; IPA HBM GB/s vs peak"
 WEIGHT_SEED = 114514
+# (complexes per GPU, pocket residues, peptide residues)
+CONFIGS = {"cfg4": (64, 256, 15), "cfg2": (64, 128, 12), "cfg1": (1, 80, 10), "cfg3": (32, 96, 12)}
 
 
 def parse_args():
@@ -35,17 +38,29 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="complexes per GPU (cfg4: 512 over 8 GPUs)")
-    ap.add_argument("--pocket", type=int, default=256)
-    ap.add_argument("--peptide", type=int, default=15)
-    ap.add_argument("--cpu-batch", type=int, default=2, help="complexes in the bounded CPU-baseline sample")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
+                    help="BASELINE.json shape: cfg4 (default) 64 x (256+15) per GPU; cfg2 64 x (128+12); stand-ins for the "
+                         "asset-bound configs: cfg1 one complex of 80+10, cfg3 32 x (96+12)")
+    ap.add_argument("--batch", type=int, default=None, help="complexes per GPU (cfg4: 512 over 8 GPUs)")
+    ap.add_argument("--pocket", type=int, default=None)
+    ap.add_argument("--peptide", type=int, default=None)
+    ap.add_argument("--cpu-batch", type=int, default=4, help="complexes in the bounded CPU-baseline sample (SURVEY 8d: 4)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="timed Euler iterations replay the captured CUDA graph (auto: on for small batches, where the "
+                         "step is launch-bound; off keeps the in-region per-kernel events of the roofline)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ipa-impl", type=int, default=None, help="kernel variant switch (pf_set_option), diagnostics only")
     ap.add_argument("--edge-impl", type=int, default=None)
     ap.add_argument("--gemm-impl", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-euler-steps", type=int, default=EULER_STEPS)
-    return ap.parse_args()
+    ap.add_argument("--edge-terms", type=int, default=None, help="pf_set_option('edge_terms'), diagnostics only")
+    args = ap.parse_args()
+    b, lr, lp = CONFIGS[args.config or "cfg4"]
+    args.batch = b if args.batch is None else args.batch
+    args.pocket = lr if args.pocket is None else args.pocket
+    args.peptide = lp if args.peptide is None else args.peptide
+    return args
 
 
 def measured_peaks():
@@ -101,33 +116,35 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def load_weights():
+    """(state_dict, description): $PEPFLOW_CKPT (the reference's model1.pt / model2.pt, loaded unchanged) or the
+    deterministic non-degenerate filler.  No product import - both arms call this."""
+    import benchdata
+    ckpt = os.environ.get("PEPFLOW_CKPT")
+    if ckpt and os.path.exists(ckpt):
+        sd = torch.load(ckpt, map_location="cpu", weights_only=False)["model"]
+        return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}, os.path.basename(ckpt)
+    return benchdata.reference_state_dict(WEIGHT_SEED), f"deterministic random init (seed {WEIGHT_SEED}, non-zero 'final' layers)"
+
+
 def make_model(device):
     from pepflowww_b200.config import load_config
     from pepflowww_b200.flow_model import FlowModel
-    from pepflowww_b200.utils import deterministic_state_dict
     cfg, _ = load_config()
     model = FlowModel(cfg.model).eval()
-    ckpt = os.environ.get("PEPFLOW_CKPT")
-    if ckpt and os.path.exists(ckpt):       # the reference's model1.pt / model2.pt load unchanged
-        from pepflowww_b200.utils import process_dic
-        model.load_state_dict(process_dic(torch.load(ckpt, map_location="cpu")["model"]))
-        weights = os.path.basename(ckpt)
-    else:
-        model.load_state_dict(deterministic_state_dict(model.state_dict(), WEIGHT_SEED))
-        weights = f"deterministic random init (seed {WEIGHT_SEED}, non-zero 'final' layers)"
-    return (model.to(device) if device is not None else model), weights
+    sd, weights = load_weights()
+    model.load_state_dict(sd)
+    return model.to(device), weights
 
 
 def cpu_baseline(args, steps, warmup):
     """The oracle port of the reference algorithm on the host cores: encode + `steps` Euler iterations of a
     bounded sample (cpu_batch complexes of the same shape); 200-step time = encode + 200 x mean step."""
+    from benchdata import synthetic_batch, torsions_mask
     from oracle import pepflow_oracle as orc
-    from pepflowww_b200.constants import torsions_mask
-    from pepflowww_b200.pep_dataloader import synthetic_batch
     torch.set_num_threads(os.cpu_count() or 1)
-    model, _ = make_model(None)
-    sd = {k: v.detach() for k, v in model.state_dict().items()}
-    batch = synthetic_batch(args.cpu_batch, args.pocket, args.peptide, seed=0)
+    sd, _ = load_weights()
+    batch = synthetic_batch(min(args.cpu_batch, args.batch), args.pocket, args.peptide, seed=0)
     B, L = batch["aa"].shape
     with torch.no_grad():
         t0 = time.perf_counter()
@@ -183,11 +200,14 @@ def run_reference(args):
 
 
 def cfg_name(args):
-    """BASELINE.json config the shape corresponds to (cfg4 = the headline 256 + 15 residue shard, cfg2 = 128 + 12)."""
-    if (args.pocket, args.peptide) == (256, 15):
-        return "cfg4"
-    if (args.pocket, args.peptide) == (128, 12):
-        return "cfg2"
+    """BASELINE.json config the shape corresponds to (cfg4 = the headline 256 + 15 residue shard, cfg2 = 128 + 12;
+    cfg1 / cfg3 need assets that do not exist offline and run on synthetic stand-ins of matching shape)."""
+    for name, (b, lr, lp) in CONFIGS.items():
+        if (args.batch, args.pocket, args.peptide) == (b, lr, lp):
+            return name + (" (synthetic stand-in)" if name in ("cfg1", "cfg3") else "")
+    for name, (b, lr, lp) in CONFIGS.items():
+        if name in ("cfg4", "cfg2") and (args.pocket, args.peptide) == (lr, lp):
+            return name
     return "custom"
 
 
@@ -232,7 +252,7 @@ def run_ours(args):
     def max_over_ranks(x):
         return _max_over_ranks(x, dev)
 
-    for name in ("ipa_impl", "edge_impl", "gemm_impl"):
+    for name in ("ipa_impl", "edge_impl", "gemm_impl", "edge_terms"):
         if getattr(args, name) is not None:
             _lib.set_option(name, getattr(args, name))
     model, weights = make_model(dev)
@@ -243,10 +263,11 @@ def run_ours(args):
     host_batch = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
     L = args.pocket + args.peptide
     hbm_peak, tensor_peak, peak_src = measured_peaks()
+    use_graph = args.graph == "on" or (args.graph == "auto" and B * L * L < 16 * 140 * 140)
 
     # ---------------- device-resident timing of K Euler iterations
     batch = recursive_to(host_batch, dev)
-    smp = model.sampler_init(batch, num_steps=EULER_STEPS, seed=1234 + rank)
+    smp = model.sampler_init(batch, num_steps=EULER_STEPS, seed=1234 + rank, graph=use_graph)
     torch.cuda.synchronize()
     for n in range(W):
         smp.step(n)
@@ -255,7 +276,7 @@ def run_ours(args):
     clocks.start()
     _lib.reset_launch_count()
     _lib.profile_read()
-    _lib.profile_enable(True)
+    _lib.profile_enable(not use_graph)       # the per-kernel events cannot be recorded inside a graph replay
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for n in range(W, W + K):
@@ -263,16 +284,35 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count()
+    launches = _lib.launch_count() if not use_graph else K * int(smp.launches_per_step or 0)
     _lib.profile_enable(False)
     prof = _lib.profile_read()
     clk = clocks.stop()
     ms_step = max_over_ranks(ms_total / K)
     value = n_gpus * B / (EULER_STEPS * ms_step / 1e3)
+    prof_ms = ms_total
+    if use_graph:
+        # kernel durations for the roofline from a separate direct-launch pass of the same iterations
+        smp2 = model.sampler_init(batch, num_steps=EULER_STEPS, seed=1234 + rank, graph=False)
+        smp2.step(0)
+        torch.cuda.synchronize()
+        _lib.profile_read()
+        _lib.profile_enable(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for n in range(1, 1 + min(K, 10)):
+            smp2.step(n)
+        p1.record()
+        torch.cuda.synchronize()
+        _lib.profile_enable(False)
+        prof = _lib.profile_read()
+        prof_ms = p0.elapsed_time(p1)
+        del smp2
 
     # roofline of the fused IPA attention kernel (256 L^2 + 21168 L bytes per complex)
     ipa_ms, ipa_n = prof["ipa"]
     edge_ms, edge_n = prof["edge"]
+    pack_ms, pack_n = prof["ipa_pack"]
     ipa_bytes = (256.0 * L * L + 21168.0 * L) * B
     roofline = None
     if ipa_n:
@@ -280,32 +320,67 @@ def run_ours(args):
         roofline = {"kernel": "ipa_attention", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak,
                     "traffic": ncu_traffic("ipa_attention", _lib.get_option("ipa_impl"), B, L), "peak_source": peak_src,
-                    "avg_launch_ms": ipa_ms / ipa_n, "launches": ipa_n, "share_of_step": ipa_ms / ms_total,
-                    "algorithmic_bytes_per_launch": ipa_bytes}
+                    "avg_launch_ms": ipa_ms / ipa_n, "launches": ipa_n, "share_of_step": ipa_ms / prof_ms,
+                    "algorithmic_bytes_per_launch": ipa_bytes,
+                    "timed": "CUDA events around every launch inside the timed region" if not use_graph else
+                             "CUDA events around every launch in a separate direct-launch pass (timed region replays a graph)"}
+        if pack_n:
+            # the operand packers move bytes the algorithmic figure does not contain: the same bytes over attention +
+            # packers is the fraction the fused-IPA op as a whole achieves
+            with_p = ipa_bytes / ((ipa_ms / ipa_n + pack_ms / pack_n) * 1e-3) / 1e9
+            roofline["with_packers"] = {"achieved": with_p, "frac": with_p / hbm_peak, "packers_ms": pack_ms / pack_n,
+                                        "share_of_step": (ipa_ms + pack_ms) / prof_ms}
     roofline_edge = None
     if edge_n:
         # Algorithmic FLOPs of the restated algorithm: the per-residue parts of W1 x and W_f x
         # are hoisted out of the pair loop, leaving 2 * (64*192 + 192*192 + 192*64 + 64*64) = 131,072 FLOP per pair
         # (the reference's literal formula is 172,032).  Split precision issues each product three times on the
-        # fp16 tensor path, so the peak to compare with is the measured dense bf16/fp16 rate / 3.
-        passes = 3 if _lib.get_option("edge_impl") in (1, 2) else 1
+        # fp16 tensor path (less where "edge_terms" drops a product), so the peak to compare with is the measured
+        # dense bf16/fp16 rate / passes.
+        terms = _lib.get_option("edge_terms")
+        gemm_flops = (64 * 192, 64 * 64, 192 * 192, 192 * 64)
+        passes = 1.0
+        if _lib.get_option("edge_impl") in (1, 2):
+            passes = sum(f * (2 if (terms >> g) & 1 and _lib.get_option("edge_impl") == 2 else 3)
+                         for g, f in enumerate(gemm_flops)) / float(sum(gemm_flops))
         flops = 131072.0 * L * L * B
         ach = flops / (edge_ms / edge_n * 1e-3) / 1e12
-        roofline_edge = {"kernel": "edge_transition", "bound": "tensor" if passes == 3 else "fp32-fma",
+        roofline_edge = {"kernel": "edge_transition", "bound": "tensor" if passes > 1 else "fp32-fma",
                          "achieved": ach, "peak": tensor_peak / passes, "unit": "TFLOP/s",
                          "frac": ach / (tensor_peak / passes),
+                         "achieved_literal_172032": ach * 172032.0 / 131072.0,
+                         "frac_literal_172032": ach * 172032.0 / 131072.0 / (tensor_peak / passes),
                          "traffic": ncu_traffic("edge_transition", _lib.get_option("edge_impl"), B, L),
-                         "peak_source": peak_src,
-                         "note": f"algorithmic fp32-equivalent FLOPs (131,072 per pair after hoisting; 172,032 in the "
-                                 f"reference's literal formula); peak = sustained bf16 / {passes} split-precision passes",
+                         "peak_source": peak_src, "split_passes": passes, "edge_terms": terms,
+                         "note": "algorithmic fp32-equivalent FLOPs: 131,072 per pair after hoisting the per-residue "
+                                 "terms (achieved / frac), 172,032 in the reference's literal formula (*_literal_172032); "
+                                 "peak = sustained bf16 / split-precision passes",
                          "executed_tensor_tflops": ach * passes,
-                         "avg_launch_ms": edge_ms / edge_n, "launches": edge_n, "share_of_step": edge_ms / ms_total}
+                         "avg_launch_ms": edge_ms / edge_n, "launches": edge_n, "share_of_step": edge_ms / prof_ms}
+
+    # ---------------- the whole FlowModel.sample, device-resident batch (no extrapolation): encode + 200 iterations
+    del smp
+    torch.cuda.empty_cache()
+    sample_wall = None
+    if not args.no_e2e:
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        smp = model.sampler_init(batch, num_steps=args.e2e_euler_steps, seed=5 + rank)
+        for n in range(args.e2e_euler_steps):
+            smp.step(n)
+        s1.record()
+        barrier()
+        t_full = max_over_ranks(s0.elapsed_time(s1) / 1e3) * (EULER_STEPS / args.e2e_euler_steps)
+        sample_wall = {"value": n_gpus * B / t_full, "unit": "peptides/s", "seconds": t_full,
+                       "what": "encode + %d Euler iterations (graph replay) on a device-resident batch, trajectory left "
+                               "in HBM; measured, not extrapolated" % args.e2e_euler_steps}
+        del smp
+        torch.cuda.empty_cache()
 
     # ---------------- end to end through the public API, host batch -> host trajectory
     e2e = None
     if not args.no_e2e:
-        del smp
-        torch.cuda.empty_cache()
         # warm-up at full size: the pinned host blocks of the dropped trajectory are recycled by the timed call
         warm = model.sample(recursive_to(host_batch, dev), num_steps=args.e2e_euler_steps, seed=7)
         del warm
@@ -324,8 +399,8 @@ def run_ours(args):
         e2e = {"value": n_gpus * B / (wall * scale), "unit": "peptides/s",
                "h2d_bytes_per_step": h2d / args.e2e_euler_steps, "d2h_bytes_per_step": d2h / args.e2e_euler_steps,
                "wall_s": wall, "euler_steps": args.e2e_euler_steps,
-               "api": "FlowModel.sample(batch, num_steps=%d): pinned host batch -> device, encode, Euler loop, "
-                      "trajectory -> host" % args.e2e_euler_steps}
+               "api": "FlowModel.sample(batch, num_steps=%d): pinned host batch -> device, encode, Euler loop (one CUDA "
+                      "graph replay per iteration), trajectory -> host" % args.e2e_euler_steps}
         del traj
 
     cb = None
@@ -338,13 +413,19 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{cfg_name(args)}: {B} complexes/GPU x {n_gpus} GPU, {args.pocket}-res pocket / "
                                        f"{args.peptide}-res peptide (L={L}), {EULER_STEPS} Euler steps",
-                           "step": "one Euler iteration (GAEncoder.forward + post-processing + manifold update) over "
-                                   "the per-GPU batch; value = complexes / (200 x step time)",
+                           "step": "one Euler iteration (GAEncoder.forward + post-processing + manifold update = one "
+                                   "pf_sampler_step call) over the per-GPU batch, state resident in HBM; value = complexes "
+                                   "/ (200 x step time); sample_wall = the whole 200-iteration sample measured; e2e = the "
+                                   "same from / to host memory (the headline)",
                            "global_batch": B * n_gpus, "parallelism": f"complexes sharded over {n_gpus} GPU(s), no collective",
-                           "weights": weights,
-                           "l2": "inputs larger than L2 (pair tensor z = %.2f GB per pass)" % (B * L * L * 256 / 1e9),
-                           "kernels": {k: _lib.get_option(k) for k in ("edge_impl", "gemm_impl", "ipa_impl")}},
-                "clocks": clk, "gpu_launches": launches, "e2e": e2e, "roofline": roofline,
+                           "weights": weights, "graph_replay_in_timed_steps": use_graph,
+                           "launches_per_step": (launches // K) if K else None,
+                           "l2": "inputs larger than L2 (pair tensor z = %.2f GB per pass)" % (B * L * L * 256 / 1e9)
+                                 if B * L * L * 256 > 126e6 else
+                                 "pair tensor z = %.1f MB per pass fits L2 (small-batch stand-in; every pass rewrites it)"
+                                 % (B * L * L * 256 / 1e6),
+                           "kernels": {k: _lib.get_option(k) for k in ("edge_impl", "gemm_impl", "ipa_impl", "edge_terms")}},
+                "clocks": clk, "gpu_launches": launches, "e2e": e2e, "sample_wall": sample_wall, "roofline": roofline,
                 "roofline_edge_transition": roofline_edge, "cpu_baseline": cb}
         print(json.dumps(line), flush=True)
     if world > 1:

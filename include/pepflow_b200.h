@@ -40,7 +40,8 @@ typedef enum pf_status {
 } pf_status;
 
 /* ---- library ---------------------------------------------------------------------------- */
-int pf_version(void);                       /* ABI version (this header: 3; 3 added the post-sampling entry points) */
+int pf_version(void);                       /* ABI version (this header: 4; 4 added pf_sampler_step, pf_zero_center,
+                                               pf_seq_transformer_forward and the "edge_terms" option) */
 const char* pf_strerror(int status);
 int pf_init(int device);                    /* opt kernels into >48 KB shared memory, query SMs */
 int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_points, int no_v_points,
@@ -62,6 +63,9 @@ int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_poin
  *                default), 0 = one GEMM / LayerNorm launch per layer
  *   "pack_impl" : IPA operand packing for ipa_impl 3 / 4: 1 = persistent double-buffered kernel (bulk copies of the
  *                next key tile under the conversion of the current one; default), 0 = one CTA per key tile
+ *   "edge_terms": split-precision products the tcgen05 edge kernel issues per GEMM (error budget:
+ *                profiles/r2_edge_error_budget.txt).  Bit g (0: z W1z^T, 1: z Wfz^T, 2: h1 W2^T, 3: h2 Wf^T) set =
+ *                that GEMM drops its A_hi W_lo product (two passes instead of three).  Default 0: three passes everywhere.
  */
 int pf_set_option(const char* name, int value);
 int pf_get_option(const char* name);
@@ -74,6 +78,9 @@ void pf_reset_launch_count(void);
  * recorded events, returns the summed durations / launch counts since the last read, and resets. */
 int pf_profile_enable(int on);
 int pf_profile_read(double* ipa_ms, int64_t* ipa_launches, double* edge_ms, int64_t* edge_launches);
+/* One category at a time: 0 = IPA attention, 1 = edge transition, 2 = the IPA operand packers (each pack launch group
+ * of a block counts as one "launch"). */
+int pf_profile_read_category(int category, double* ms, int64_t* launches);
 
 /* Diagnostics: while a device buffer is registered, instrumented kernel variants write clock64() stamps of
  * their internal hand-offs into it (layout documented at the kernel).  NULL unregisters.  Not a hot-path call. */
@@ -213,6 +220,47 @@ int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* r
                           const float* edge_embed, const float* res_mask, float* pred_rot, float* pred_trans,
                           float* pred_angles, float* logits, float* node_out, void* workspace,
                           size_t workspace_bytes, int B, int L, void* stream);
+
+/* The sequence-transformer seam of one block (torch.nn.TransformerEncoder of ga.py:53-62 called at :105-106):
+ * y[B,L,128] = the two post-norm encoder layers of block `block` applied to x[B,L,128] with key-padding mask
+ * res_mask[B,L] - the same fused layer chains and attention kernel the composite launches.  workspace as
+ * pf_ga_encoder_forward (needs w->prepacked). */
+int pf_seq_transformer_forward(const pf_ga_weights* w, int block, const float* x, const float* res_mask, float* y,
+                               void* workspace, size_t workspace_bytes, int B, int L, void* stream);
+
+/* ---- one whole iteration of the FlowModel.sample loop (models_con/flow_model.py:287-343, last one :346-372) ----
+ * State, trajectory and the iteration counter live on the device and every argument is the same for all iterations,
+ * so one call (denoiser + post-processing + manifold Euler update, 73 kernels) can be captured in a CUDA graph once
+ * and replayed num_steps times.  Iteration n = step[0] at the time the call executes: t = ts[n]; the clean prediction
+ * goes to trajectory slot n; the state advances by d_t = ts[n+1] - ts[n] unless n is the last iteration; step[0]
+ * becomes n + 1.  Categorical draws: uniforms[n][0 | 1][B*L] when given, else Philox4x32-10(seed, 2n | 2n+1, residue).
+ * sample_bb / sample_ang / sample_seq = 0 pin that modality to the ground truth (:306-311, :336-342). */
+typedef struct pf_sampler {
+  const pf_ga_weights* weights;
+  const float* node_embed; const float* edge_embed; const float* res_mask;     /* [B,L,128] [B,L,L,64] [B,L]       */
+  void* workspace; uint64_t workspace_bytes;                                   /* pf_ga_encoder_workspace_bytes     */
+  const float* rot1; const float* trans1; const float* ang1; const int64_t* seq1;   /* ground truth / context      */
+  const uint8_t* gen_mask; const float* torsions_mask;                         /* [B,L] u8; [22,5]                  */
+  const float* trans0; const float* simplex0;                                  /* initial noise x_0, simplex_0      */
+  float* rot_t; float* trans_t; float* ang_t; int64_t* seq_t; float* simplex_t;     /* state, updated in place     */
+  float* pred_rot; float* pred_trans; float* pred_ang; float* logits;          /* scratch: denoiser outputs         */
+  float* traj_rot; float* traj_trans; float* traj_ang; int64_t* traj_seq; float* traj_simplex;  /* [num_steps,...]  */
+  const float* ts;                                                             /* [num_steps] time grid             */
+  const float* uniforms;                                                       /* [num_steps,2,B,L] or NULL         */
+  int32_t* step;                                                               /* [2]: next iteration, scratch      */
+  float* t_cur;                                                                /* [B] scratch                       */
+  uint64_t seed;
+  int32_t num_steps, B, L;
+  int32_t sample_bb, sample_ang, sample_seq;
+  float simplex_k;
+  int32_t reserved;
+} pf_sampler;
+int pf_sampler_step(const pf_sampler* s, void* stream);
+
+/* FlowModel.zero_center_part (models_con/flow_model.py:95-106), in place: pos[B,L,3] <- (pos - c_b) * res_mask with
+ * c_b = sum_l pos * gen_mask / (sum_l gen_mask + 1e-8); center_out[B,3] optional. */
+int pf_zero_center(float* pos, const uint8_t* gen_mask, const float* res_mask, float* center_out, int B, int L,
+                   void* stream);
 
 /* ---- once-per-sample pair embedder -------------------------------------------
  * EdgeEmbedder.forward, models_con/edge.py:39-112, fused: atom coordinates -> [N, L, L, 64] pair features in one

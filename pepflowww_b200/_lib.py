@@ -32,6 +32,7 @@ SIGNATURES = {
     "pf_ga_prepack": (_i, [_p, _p, _sz, _p]),
     "pf_profile_enable": (_i, [_i]),
     "pf_profile_read": (_i, [_p, _p, _p, _p]),
+    "pf_profile_read_category": (_i, [_i, _p, _p]),
     "pf_linear": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "pf_linear_workspace_bytes": (_sz, [_i]),
     "pf_linear_ws": (_i, [_p] * 6 + [_i] * 4 + [_p, _sz, _p]),
@@ -59,6 +60,9 @@ SIGNATURES = {
     "pf_full_atom_reconstruction": (_i, [_p] * 13 + [C.c_longlong, _p]),
     "pf_reconstruct_backbone": (_i, [_p] * 9 + [_i] * 2 + [_p]),
     "pf_torsion_angles": (_i, [_p] * 5 + [C.c_longlong, _i, _p]),
+    "pf_seq_transformer_forward": (_i, [_p, _i, _p, _p, _p, _p, _sz, _i, _i, _p]),
+    "pf_sampler_step": (_i, [_p, _p]),
+    "pf_zero_center": (_i, [_p] * 4 + [_i, _i, _p]),
 }
 
 # enum sizes of include/pepflow_b200.h
@@ -82,6 +86,19 @@ class GaWeights(C.Structure):
     _fields_ = [("num_blocks", C.c_int32), ("reserved", C.c_int32),
                 ("g", _p * PF_G_NSLOTS), ("blk", (_p * PF_B_NSLOTS) * PF_MAX_BLOCKS),
                 ("prepacked", _p), ("prepacked_bytes", C.c_uint64)]
+
+
+class Sampler(C.Structure):
+    """pf_sampler of include/pepflow_b200.h (field order is the ABI)."""
+    _fields_ = ([("weights", _p), ("node_embed", _p), ("edge_embed", _p), ("res_mask", _p), ("workspace", _p),
+                 ("workspace_bytes", C.c_uint64)] +
+                [(n, _p) for n in ("rot1", "trans1", "ang1", "seq1", "gen_mask", "torsions_mask", "trans0", "simplex0",
+                                   "rot_t", "trans_t", "ang_t", "seq_t", "simplex_t", "pred_rot", "pred_trans", "pred_ang",
+                                   "logits", "traj_rot", "traj_trans", "traj_ang", "traj_seq", "traj_simplex", "ts",
+                                   "uniforms", "step", "t_cur")] +
+                [("seed", C.c_uint64), ("num_steps", C.c_int32), ("B", C.c_int32), ("L", C.c_int32),
+                 ("sample_bb", C.c_int32), ("sample_ang", C.c_int32), ("sample_seq", C.c_int32),
+                 ("simplex_k", C.c_float), ("reserved", C.c_int32)])
 
 
 _lib = None
@@ -137,8 +154,9 @@ def ptr(t, dtype=torch.float32, allow_none=False):
     return t.data_ptr()
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def stream(device=None):
+    """Raw handle of torch's current stream on `device` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def set_option(name, value):
@@ -162,8 +180,10 @@ def profile_enable(on):
 
 
 def profile_read():
-    """{'ipa': (ms, launches), 'edge': (ms, launches)} since the last read (synchronises)."""
-    a, b = C.c_double(0), C.c_double(0)
-    na, nb = C.c_int64(0), C.c_int64(0)
-    check(load().pf_profile_read(C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
-    return {"ipa": (a.value, na.value), "edge": (b.value, nb.value)}
+    """{'ipa': (ms, launches), 'edge': ..., 'ipa_pack': ...} since the last read (synchronises)."""
+    out = {}
+    for cat, name in enumerate(("ipa", "edge", "ipa_pack")):
+        ms, n = C.c_double(0), C.c_int64(0)
+        check(load().pf_profile_read_category(cat, C.byref(ms), C.byref(n)))
+        out[name] = (ms.value, n.value)
+    return out

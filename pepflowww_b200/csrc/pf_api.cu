@@ -12,15 +12,16 @@ namespace pf {
 
 static std::atomic<int64_t> g_launches{0};
 static int g_num_sms = 148;
-static std::atomic<int> g_edge_impl{2}, g_gemm_impl{2}, g_ipa_impl{4}, g_chain_impl{1}, g_pack_impl{1};
+static std::atomic<int> g_edge_impl{2}, g_gemm_impl{2}, g_ipa_impl{4}, g_chain_impl{1}, g_pack_impl{1}, g_edge_terms{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static std::atomic<int> g_profile{0};
 static std::mutex g_prof_mu;
 static std::vector<cudaEvent_t> g_ev_pool;               // reusable events
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev[2];
-static cudaEvent_t g_open[2] = {nullptr, nullptr};
+constexpr int NPROF = 3;                                  // 0 IPA attention, 1 edge transition, 2 IPA operand packers
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev[NPROF];
+static cudaEvent_t g_open[NPROF] = {nullptr, nullptr, nullptr};
 
 static cudaEvent_t take_event() {
   if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
@@ -52,6 +53,8 @@ int opt_gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
 int opt_ipa_impl() { return g_ipa_impl.load(std::memory_order_relaxed); }
 int opt_chain_impl() { return g_chain_impl.load(std::memory_order_relaxed); }
 int opt_pack_impl() { return g_pack_impl.load(std::memory_order_relaxed); }
+int opt_edge_terms() { return g_edge_terms.load(std::memory_order_relaxed); }
+void edge_umma_resolve_driver();
 
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -151,7 +154,7 @@ static size_t enumerate_packables(const pf_ga_weights* w, std::vector<PackItem>*
 
 extern "C" {
 
-int pf_version(void) { return 3; }
+int pf_version(void) { return 4; }
 
 size_t pf_ga_prepack_bytes(const pf_ga_weights* w) {
   if (!w || w->num_blocks < 1 || w->num_blocks > PF_MAX_BLOCKS) return 0;
@@ -214,6 +217,8 @@ const char* pf_strerror(int status) {
 int pf_init(int device) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return PF_ERR_NO_DEVICE;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return static_cast<int>(e);
   int sms = 0;
@@ -227,7 +232,9 @@ int pf_init(int device) {
   pf::edge_kernels_init();
   pf::gemm_umma_init();
   pf::embed_kernels_init();
+  pf::edge_umma_resolve_driver();
   e = cudaGetLastError();
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);   // the caller's current device is left as it was
   return e == cudaSuccess ? PF_OK : static_cast<int>(e);
 }
 
@@ -245,6 +252,7 @@ int pf_set_option(const char* name, int value) {
   if (!std::strcmp(name, "ipa_impl") && (value >= 0 && value <= 4)) { pf::g_ipa_impl = value; return PF_OK; }
   if (!std::strcmp(name, "chain_impl") && (value >= 0 && value <= 1)) { pf::g_chain_impl = value; return PF_OK; }
   if (!std::strcmp(name, "pack_impl") && (value >= 0 && value <= 1)) { pf::g_pack_impl = value; return PF_OK; }
+  if (!std::strcmp(name, "edge_terms") && (value >= 0 && value <= 15)) { pf::g_edge_terms = value; return PF_OK; }
   return PF_ERR_BAD_OPTION;
 }
 
@@ -255,6 +263,7 @@ int pf_get_option(const char* name) {
   if (!std::strcmp(name, "ipa_impl")) return pf::opt_ipa_impl();
   if (!std::strcmp(name, "chain_impl")) return pf::opt_chain_impl();
   if (!std::strcmp(name, "pack_impl")) return pf::opt_pack_impl();
+  if (!std::strcmp(name, "edge_terms")) return pf::opt_edge_terms();
   return PF_ERR_BAD_OPTION;
 }
 
@@ -269,29 +278,31 @@ int pf_profile_enable(int on) {
   return PF_OK;
 }
 
-int pf_profile_read(double* ipa_ms, int64_t* ipa_launches, double* edge_ms, int64_t* edge_launches) {
+int pf_profile_read_category(int category, double* ms_out, int64_t* launches_out) {
+  if (category < 0 || category >= pf::NPROF) return PF_ERR_BAD_OPTION;
   std::lock_guard<std::mutex> lk(pf::g_prof_mu);
-  double ms[2] = {0.0, 0.0};
-  int64_t cnt[2] = {0, 0};
-  for (int c = 0; c < 2; ++c) {
-    for (auto& pr : pf::g_ev[c]) {
-      cudaError_t e = cudaEventSynchronize(pr.second);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      float t = 0.f;
-      e = cudaEventElapsedTime(&t, pr.first, pr.second);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      ms[c] += t;
-      ++cnt[c];
-      pf::g_ev_pool.push_back(pr.first);
-      pf::g_ev_pool.push_back(pr.second);
-    }
-    pf::g_ev[c].clear();
+  double ms = 0.0;
+  int64_t cnt = 0;
+  for (auto& pr : pf::g_ev[category]) {
+    cudaError_t e = cudaEventSynchronize(pr.second);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    float t = 0.f;
+    e = cudaEventElapsedTime(&t, pr.first, pr.second);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    ms += t;
+    ++cnt;
+    pf::g_ev_pool.push_back(pr.first);
+    pf::g_ev_pool.push_back(pr.second);
   }
-  if (ipa_ms) *ipa_ms = ms[0];
-  if (ipa_launches) *ipa_launches = cnt[0];
-  if (edge_ms) *edge_ms = ms[1];
-  if (edge_launches) *edge_launches = cnt[1];
+  pf::g_ev[category].clear();
+  if (ms_out) *ms_out = ms;
+  if (launches_out) *launches_out = cnt;
   return PF_OK;
+}
+
+int pf_profile_read(double* ipa_ms, int64_t* ipa_launches, double* edge_ms, int64_t* edge_launches) {
+  PF_TRY(pf_profile_read_category(0, ipa_ms, ipa_launches));
+  return pf_profile_read_category(1, edge_ms, edge_launches);
 }
 
 int64_t pf_launch_count(void) { return pf::g_launches.load(); }
@@ -300,6 +311,59 @@ void pf_reset_launch_count(void) { pf::g_launches.store(0); }
 size_t pf_ga_encoder_workspace_bytes(int B, int L) {
   if (B <= 0 || L <= 0) return 256;
   return pf::carve(nullptr, B, L).total;
+}
+
+int pf_seq_transformer_forward(const pf_ga_weights* w, int block, const float* x, const float* res_mask, float* y,
+                               void* workspace, size_t workspace_bytes, int B, int L, void* stream) {
+  using namespace pf;
+  PF_REQUIRE(w && x && res_mask && y && workspace, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(B >= 0 && L >= 0, PF_ERR_BAD_SHAPE);
+  PF_REQUIRE(w->num_blocks >= 1 && w->num_blocks <= PF_MAX_BLOCKS && block >= 0 && block < w->num_blocks, PF_ERR_BAD_CONFIG);
+  if (B == 0 || L == 0) return PF_OK;
+  PF_REQUIRE(aligned16(workspace) && aligned16(x) && aligned16(y), PF_ERR_MISALIGNED);
+  const GaWorkspace ws = carve(workspace, B, L);
+  PF_REQUIRE(workspace_bytes >= ws.total, PF_ERR_WORKSPACE_TOO_SMALL);
+  std::vector<PackItem> packed;
+  PF_REQUIRE(w->prepacked && w->prepacked_bytes >= enumerate_packables(w, nullptr), PF_ERR_BAD_CONFIG);
+  enumerate_packables(w, &packed);
+  const float* const* W = w->blk[block];
+  for (int i = PF_B_T0_IN_W; i <= PF_B_T1_N2_B; ++i) PF_REQUIRE(W[i], PF_ERR_NULL_POINTER);
+  cudaStream_t st = as_stream(stream);
+  const int M = B * L;
+  auto stage = [&](const float* wt, const float* bias, int N, int act) {
+    NodeChainStage c{};
+    for (const PackItem& it : packed)
+      if (it.w == wt && !it.edge && it.kind != 2) c.wpack = static_cast<const unsigned char*>(w->prepacked) + it.off;
+    c.bias = bias; c.N = N; c.act = act;
+    return c;
+  };
+  auto run_chain = [&](const float* x0, std::vector<NodeChainStage>& c) -> int {
+    for (const NodeChainStage& q : c) PF_REQUIRE(q.wpack, PF_ERR_BAD_CONFIG);
+    return launch_node_chain(x0, M, c.data(), (int)c.size(), st);
+  };
+  const float* in = x;
+  for (int l = 0; l < 2; ++l) {
+    const int o = l == 0 ? PF_B_T0_IN_W : PF_B_T1_IN_W;
+    {
+      std::vector<NodeChainStage> c;
+      NodeChainStage q = stage(W[o], W[o + 1], 384, 0); q.out = ws.qkv;                // in_proj
+      c.push_back(q);
+      PF_TRY(run_chain(in, c));
+    }
+    PF_TRY(launch_seq_attention(ws.qkv, res_mask, ws.ctx, B, L, st));
+    std::vector<NodeChainStage> c;
+    NodeChainStage q = stage(W[o + 2], W[o + 3], 128, 0);                              // out_proj, norm1(x + .)
+    q.res = in; q.gamma = W[o + 8]; q.beta = W[o + 9]; q.save_res = q.next_a = true;
+    c.push_back(q);
+    q = stage(W[o + 4], W[o + 5], 128, 1); q.next_a = true;                            // linear1 + relu
+    c.push_back(q);
+    q = stage(W[o + 6], W[o + 7], 128, 0);                                             // linear2, norm2(y + .)
+    q.res_from_chain = true; q.gamma = W[o + 10]; q.beta = W[o + 11]; q.out = l == 0 ? ws.ya : y;
+    c.push_back(q);
+    PF_TRY(run_chain(ws.ctx, c));
+    in = ws.ya;
+  }
+  return PF_OK;
 }
 
 int pf_ga_encoder_forward(const pf_ga_weights* w, const float* t, const float* rot_t, const float* trans_t,

@@ -34,6 +34,7 @@ int opt_gemm_impl();
 int opt_ipa_impl();
 int opt_chain_impl();
 int opt_pack_impl();
+int opt_edge_terms();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

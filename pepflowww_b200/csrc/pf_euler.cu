@@ -255,6 +255,194 @@ __global__ void euler_step_kernel(EulerArgs a) {
   }
 }
 
+
+// ---- one whole loop iteration with device-resident bookkeeping (pf_sampler_step) -----------------------------------
+// sampler_begin_kernel: n = step[0] is the iteration this call executes: t_cur[b] = ts[n], step[1] = n, step[0] = n + 1.
+__global__ void sampler_begin_kernel(int* __restrict__ step, const float* __restrict__ ts, float* __restrict__ t_cur,
+                                     int B, int num_steps) {
+  int n = step[0];
+  n = n < 0 ? 0 : (n > num_steps - 1 ? num_steps - 1 : n);
+  const float t = ts[n];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) t_cur[b] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) { step[1] = n; step[0] = n + 1; }
+}
+
+constexpr int SU_T = 128;            // residues per CTA
+constexpr int SU_PITCH = 21;         // staging pitch of the 20-wide rows (odd: conflict-free row-per-thread access)
+
+struct SamplerArgs {
+  const float* pred_rot; const float* pred_trans; const float* pred_ang; const float* logits;
+  const float* rot1; const float* trans1; const float* ang1; const int64_t* seq1; const uint8_t* gen;
+  const float* tmask; const float* trans0; const float* simplex0;
+  float* rot_t; float* trans_t; float* ang_t; int64_t* seq_t; float* simplex_t;
+  float* traj_rot; float* traj_trans; float* traj_ang; int64_t* traj_seq; float* traj_simplex;
+  const float* ts; const float* uniforms; const int* step;
+  uint64_t seed;
+  int n, num_steps;                  // n = B * L residues
+  int sample_bb, sample_ang, sample_seq;
+  float k;
+};
+
+// Rows of W floats cross HBM as contiguous, fully coalesced runs of the CTA's 128-residue tile (staged in shared
+// memory); every thread then owns one residue in registers.
+template <int W, int P>
+__device__ __forceinline__ void su_load(float* stage, const float* __restrict__ g, int r0, int nr, float (&v)[W]) {
+  __syncthreads();
+  const float* src = g + (size_t)r0 * W;
+  for (int e = threadIdx.x; e < nr * W; e += SU_T) stage[(e / W) * P + (e % W)] = src[e];
+  __syncthreads();
+  if ((int)threadIdx.x < nr) {
+#pragma unroll
+    for (int e = 0; e < W; ++e) v[e] = stage[threadIdx.x * P + e];
+  }
+}
+template <int W, int P>
+__device__ __forceinline__ void su_store(float* stage, float* __restrict__ g, int r0, int nr, const float (&v)[W]) {
+  __syncthreads();
+  if ((int)threadIdx.x < nr) {
+#pragma unroll
+    for (int e = 0; e < W; ++e) stage[threadIdx.x * P + e] = v[e];
+  }
+  __syncthreads();
+  float* dst = g + (size_t)r0 * W;
+  for (int e = threadIdx.x; e < nr * W; e += SU_T) dst[e] = stage[(e / W) * P + (e % W)];
+}
+
+// Post-processing of the denoiser output into trajectory slot n (flow_model.py:291-314) and the Euler update of the
+// state (:316-343), one residue per thread.
+__global__ void __launch_bounds__(SU_T) sampler_update_kernel(SamplerArgs a) {
+  __shared__ float stage[SU_T * SU_PITCH];
+  __shared__ float s_tmask[22 * 5];
+  const int r0 = blockIdx.x * SU_T;
+  const int nr = min(SU_T, a.n - r0);
+  const int i = r0 + threadIdx.x;
+  const bool on = (int)threadIdx.x < nr;
+  if (threadIdx.x < 110) s_tmask[threadIdx.x] = a.tmask[threadIdx.x];
+  const int n = a.step[1];
+  const size_t slot = (size_t)n * a.n;            // residue offset of trajectory slot n
+  const bool g = on && a.gen[i] != 0;
+  const int64_t s1 = on ? a.seq1[i] : 0;
+
+  float c_rot[9], c_trans[3], c_ang[5], rot1[9], trans1[3], ang1[5];
+  su_load<9, 9>(stage, a.rot1, r0, nr, rot1);
+  su_load<3, 3>(stage, a.trans1, r0, nr, trans1);
+  su_load<5, 5>(stage, a.ang1, r0, nr, ang1);
+  su_load<9, 9>(stage, a.pred_rot, r0, nr, c_rot);
+  su_load<3, 3>(stage, a.pred_trans, r0, nr, c_trans);
+  su_load<5, 5>(stage, a.pred_ang, r0, nr, c_ang);
+  int64_t c_seq = s1;
+  {
+    float lg[20];
+    su_load<20, SU_PITCH>(stage, a.logits, r0, nr, lg);
+    if (g) {
+      const float* u = a.uniforms ? a.uniforms + (size_t)(2 * n) * a.n : nullptr;
+      c_seq = categorical20(lg, uniform_for(u, a.seed, (uint64_t)(2 * n), i));
+    }
+  }
+  if (!g || !a.sample_bb) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) c_rot[e] = rot1[e];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) c_trans[e] = trans1[e];
+  }
+  {
+    const int si = (c_seq >= 0 && c_seq < 22) ? (int)c_seq : 21;
+#pragma unroll
+    for (int e = 0; e < 5; ++e) c_ang[e] = (s_tmask[si * 5 + e] != 0.f) ? (g ? c_ang[e] : ang1[e]) : 0.f;
+  }
+  if (!a.sample_ang) {
+#pragma unroll
+    for (int e = 0; e < 5; ++e) c_ang[e] = ang1[e];
+  }
+  if (!a.sample_seq) c_seq = s1;
+  su_store<9, 9>(stage, a.traj_rot + slot * 9, r0, nr, c_rot);
+  su_store<3, 3>(stage, a.traj_trans + slot * 3, r0, nr, c_trans);
+  su_store<5, 5>(stage, a.traj_ang + slot * 5, r0, nr, c_ang);
+  if (on) a.traj_seq[slot + i] = c_seq;
+  {
+    float cs[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) cs[k] = (c_seq == k) ? a.k : -a.k;      // one_hot * 2k - k (flow_model.py:108-109)
+    su_store<20, SU_PITCH>(stage, a.traj_simplex + slot * 20, r0, nr, cs);
+  }
+  if (n >= a.num_steps - 1) return;               // the last iteration only records its prediction (:346-372)
+
+  const float dt = a.ts[n + 1] - a.ts[n];
+  // translations (:318-320): x_t + (x^ - x_0) d_t   -- x_0 is the initial noise
+  {
+    float xt[3], x0[3];
+    su_load<3, 3>(stage, a.trans_t, r0, nr, xt);
+    su_load<3, 3>(stage, a.trans0, r0, nr, x0);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) xt[e] = (g && a.sample_bb) ? xt[e] + (c_trans[e] - x0[e]) * dt : trans1[e];
+    su_store<3, 3>(stage, a.trans_t, r0, nr, xt);
+  }
+  // rotations (:322-323): geodesic with the fixed 10 d_t schedule
+  {
+    float Rt[9], O[9];
+    su_load<9, 9>(stage, a.rot_t, r0, nr, Rt);
+    const bool live = g && a.sample_bb;
+    if (live) so3_geodesic_dev(dt * 10.0f, c_rot, Rt, O);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) O[e] = live ? O[e] : rot1[e];
+    su_store<9, 9>(stage, a.rot_t, r0, nr, O);
+  }
+  // simplex + residue types (:328-330); no where() on the simplex
+  int64_t s2 = s1;
+  {
+    float sx[20], s0[20];
+    su_load<20, SU_PITCH>(stage, a.simplex_t, r0, nr, sx);
+    su_load<20, SU_PITCH>(stage, a.simplex0, r0, nr, s0);
+#pragma unroll
+    for (int k = 0; k < 20; ++k) sx[k] = sx[k] + (((c_seq == k) ? a.k : -a.k) - s0[k]) * dt;
+    su_store<20, SU_PITCH>(stage, a.simplex_t, r0, nr, sx);
+    if (g) {
+      const float* u = a.uniforms ? a.uniforms + (size_t)(2 * n + 1) * a.n : nullptr;
+      s2 = categorical20(sx, uniform_for(u, a.seed, (uint64_t)(2 * n + 1), i));
+    }
+  }
+  // torsions (:325-326, :332-333)
+  {
+    float at[5];
+    su_load<5, 5>(stage, a.ang_t, r0, nr, at);
+    const int si = (s2 >= 0 && s2 < 22) ? (int)s2 : 21;
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      const float v = g ? tor_geodesic_dev(dt, c_ang[e], at[e]) : ang1[e];
+      at[e] = a.sample_ang ? ((s_tmask[si * 5 + e] != 0.f) ? v : 0.f) : ang1[e];
+    }
+    su_store<5, 5>(stage, a.ang_t, r0, nr, at);
+  }
+  if (on) a.seq_t[i] = a.sample_seq ? s2 : s1;
+}
+
+// FlowModel.zero_center_part (flow_model.py:95-106): one CTA per complex
+__global__ void __launch_bounds__(256) zero_center_kernel(float* __restrict__ pos, const uint8_t* __restrict__ gen,
+                                                           const float* __restrict__ rmask, float* __restrict__ center,
+                                                           int L) {
+  __shared__ float red[4][8];
+  __shared__ float c[3];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float* p = pos + (size_t)b * L * 3;
+  float sx = 0.f, sy = 0.f, sz = 0.f, cnt = 0.f;
+  for (int l = tid; l < L; l += 256) {
+    const float m = gen[(size_t)b * L + l] ? 1.f : 0.f;
+    sx += p[l * 3] * m; sy += p[l * 3 + 1] * m; sz += p[l * 3 + 2] * m; cnt += m;
+  }
+  sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); cnt = warp_sum(cnt);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = sx; red[1][tid >> 5] = sy; red[2][tid >> 5] = sz; red[3][tid >> 5] = cnt; }
+  __syncthreads();
+  if (tid < 3) {
+    float s = 0.f, n = 0.f;
+    for (int w = 0; w < 8; ++w) { s += red[tid][w]; n += red[3][w]; }
+    c[tid] = s / (n + 1e-8f);
+    if (center) center[b * 3 + tid] = c[tid];
+  }
+  __syncthreads();
+  for (int e = tid; e < L * 3; e += 256) p[e] = (p[e] - c[e % 3]) * rmask[(size_t)b * L + e / 3];
+}
+
 }  // namespace pf
 
 extern "C" {
@@ -325,6 +513,41 @@ int pf_euler_step(const float* rot_t, const float* trans_t, const float* ang_t, 
                   rot1, trans1, ang1, seq1, gen_mask, torsions_mask, uniforms, seed, counter, d_t,
                   rot_out, trans_out, ang_out, seq_out, simplex_out, n, simplex_k};
   pf::euler_step_kernel<<<(n + 127) / 128, 128, 0, pf::as_stream(stream)>>>(a);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+int pf_sampler_step(const pf_sampler* s, void* stream) {
+  PF_REQUIRE(s && s->weights && s->node_embed && s->edge_embed && s->res_mask && s->workspace && s->rot1 && s->trans1 &&
+                 s->ang1 && s->seq1 && s->gen_mask && s->torsions_mask && s->trans0 && s->simplex0 && s->rot_t &&
+                 s->trans_t && s->ang_t && s->seq_t && s->simplex_t && s->pred_rot && s->pred_trans && s->pred_ang &&
+                 s->logits && s->traj_rot && s->traj_trans && s->traj_ang && s->traj_seq && s->traj_simplex && s->ts &&
+                 s->step && s->t_cur, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(s->B >= 0 && s->L >= 0 && s->num_steps >= 1, PF_ERR_BAD_SHAPE);
+  if (s->B == 0 || s->L == 0) return PF_OK;
+  cudaStream_t st = pf::as_stream(stream);
+  pf::sampler_begin_kernel<<<1, 128, 0, st>>>(s->step, s->ts, s->t_cur, s->B, s->num_steps);
+  PF_CHECK_LAUNCH();
+  PF_TRY(pf_ga_encoder_forward(s->weights, s->t_cur, s->rot_t, s->trans_t, s->ang_t, s->seq_t, s->node_embed,
+                               s->edge_embed, s->res_mask, s->pred_rot, s->pred_trans, s->pred_ang, s->logits, nullptr,
+                               s->workspace, (size_t)s->workspace_bytes, s->B, s->L, stream));
+  const int n = s->B * s->L;
+  pf::SamplerArgs a{s->pred_rot, s->pred_trans, s->pred_ang, s->logits, s->rot1, s->trans1, s->ang1, s->seq1,
+                    s->gen_mask, s->torsions_mask, s->trans0, s->simplex0, s->rot_t, s->trans_t, s->ang_t, s->seq_t,
+                    s->simplex_t, s->traj_rot, s->traj_trans, s->traj_ang, s->traj_seq, s->traj_simplex, s->ts,
+                    s->uniforms, s->step, s->seed, n, s->num_steps, s->sample_bb, s->sample_ang, s->sample_seq,
+                    s->simplex_k};
+  pf::sampler_update_kernel<<<(n + pf::SU_T - 1) / pf::SU_T, pf::SU_T, 0, st>>>(a);
+  PF_CHECK_LAUNCH();
+  return PF_OK;
+}
+
+int pf_zero_center(float* pos, const uint8_t* gen_mask, const float* res_mask, float* center_out, int B, int L,
+                   void* stream) {
+  PF_REQUIRE(pos && gen_mask && res_mask, PF_ERR_NULL_POINTER);
+  PF_REQUIRE(B >= 0 && L >= 0, PF_ERR_BAD_SHAPE);
+  if (B == 0 || L == 0) return PF_OK;
+  pf::zero_center_kernel<<<B, 256, 0, pf::as_stream(stream)>>>(pos, gen_mask, res_mask, center_out, L);
   PF_CHECK_LAUNCH();
   return PF_OK;
 }

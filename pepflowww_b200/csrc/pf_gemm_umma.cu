@@ -572,6 +572,7 @@ int launch_node_chain(const float* x, int M, const NodeChainStage* stages, int n
 }
 
 void gemm_umma_init() {
+  { CUtensorMap m; (void)encode_y_map(&m, reinterpret_cast<float*>(uintptr_t(1) << 20), 128, 128); }  // resolve the driver entry point outside any stream capture
   cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GU_SMEM);
   cudaFuncSetAttribute(node_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GU_SMEM);
 }

@@ -1376,6 +1376,7 @@ int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_
   unsigned char* blobs = static_cast<unsigned char*>(workspace);
   uint4* Qp = reinterpret_cast<uint4*>(blobs + (size_t)a.B * JT * V2_BLOB);
   IpaPack3Args pa{a.proj, a.rot, a.trans, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT, 0};
+  profile_begin(2, st);
   if (opt_pack_impl() == 1) {
     const int nblob = a.B * JT;
     ipa_pack4_kernel<<<nblob < num_sms() ? nblob : num_sms(), P4_THREADS, P4_SMEM, st>>>(pa);
@@ -1385,6 +1386,7 @@ int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_
   } else {
     ipa_pack3_kernel<<<(unsigned)(a.B * JT + a.B * IT), P3_THREADS, P3_SMEM, st>>>(pa);
   }
+  profile_end(2, st);
   PF_CHECK_LAUNCH();
   Ipa3Args args;
   PF_TRY(encode_z_map(&args.tm_z, a.z, a.B, a.L));

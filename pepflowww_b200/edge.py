@@ -68,15 +68,26 @@ class EdgeEmbedder(nn.Module):
                 o0.bias, o2.weight.t().contiguous(), o2.bias, o4.weight.t().contiguous(), o4.bias)
 
     def forward(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask=None, sequence_mask=None):
+        """The fused kernel (pf_edge_embed).  CUDA tensors, no autograd - there is no silent torch or CPU fallback; the
+        differentiable formulation of the training path is forward_autograd()."""
+        if not pos_atoms.is_cuda:
+            raise RuntimeError("EdgeEmbedder.forward runs the CUDA kernel (no CPU fallback); got a CPU tensor")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("EdgeEmbedder.forward runs the inference kernel; wrap the call in torch.no_grad() "
+                               "(the autograd training path is EdgeEmbedder.forward_autograd)")
+        if not (self.max_num_atoms == 15 and self.max_aa_types == 22 and self.max_relpos == 32 and
+                self.aa_pair_embed.weight.shape[1] == 64 and self.dihedral_embed.num_funcs == 3):
+            raise ValueError("pf_edge_embed is specialised to 15 atoms / 22 residue types / relpos 32 / 64 channels")
+        from . import ops
+        if sequence_mask is not None:
+            aa = torch.where(sequence_mask, aa, torch.full_like(aa, fill_value=int(AA.UNK)))
+        return ops.edge_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, self._kernel_constants())
+
+    def forward_autograd(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask=None, sequence_mask=None):
+        """Same contract in differentiable torch ops over the same parameters (models_con/edge.py:39-112): the gradient
+        path of FlowModel.forward / train_ddp.py."""
         N, L = aa.size()
         A = self.max_num_atoms
-        fused = (pos_atoms.is_cuda and not torch.is_grad_enabled() and A == 15 and self.max_aa_types == 22 and
-                 self.max_relpos == 32 and self.aa_pair_embed.weight.shape[1] == 64 and self.dihedral_embed.num_funcs == 3)
-        if fused:
-            from . import ops
-            if sequence_mask is not None:
-                aa = torch.where(sequence_mask, aa, torch.full_like(aa, fill_value=int(AA.UNK)))
-            return ops.edge_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, self._kernel_constants())
         pos_atoms, mask_atoms = pos_atoms[:, :, :A], mask_atoms[:, :, :A]
         mask_residue = mask_atoms[:, :, BBHeavyAtom.CA]
         if sequence_mask is not None:

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops, so3_utils, torus
+from . import _lib, ops, so3_utils, torus
 from .constants import BBHeavyAtom, max_num_heavyatoms, torsions_mask
 from .edge import EdgeEmbedder
 from .ga import GAEncoder
@@ -46,7 +46,9 @@ class FlowModel(nn.Module):
             raise ValueError("the Euler kernels are specialised to 20 residue classes")
 
     # ------------------------------------------------------------------ reference helpers
-    def encode(self, batch):
+    def encode(self, batch, autograd=False):
+        """flow_model.py:75-93.  autograd=False: the embedder kernels (sampling; call under torch.no_grad());
+        autograd=True: their differentiable torch formulations (FlowModel.forward's gradient path)."""
         pos = batch["pos_heavyatom"]
         rotmats_1 = construct_3d_basis(pos[:, :, BBHeavyAtom.CA], pos[:, :, BBHeavyAtom.C], pos[:, :, BBHeavyAtom.N])
         trans_1 = pos[:, :, BBHeavyAtom.CA]
@@ -56,11 +58,17 @@ class FlowModel(nn.Module):
         structure_mask = context_mask if self.sample_structure else None
         sequence_mask = context_mask if self.sample_sequence else None
         args = (batch["aa"], batch["res_nb"], batch["chain_nb"], pos, batch["mask_heavyatom"])
-        node_embed = self.node_embedder(*args, structure_mask=structure_mask, sequence_mask=sequence_mask)
-        edge_embed = self.edge_embedder(*args, structure_mask=structure_mask, sequence_mask=sequence_mask)
+        node_fn = self.node_embedder.forward_autograd if autograd else self.node_embedder
+        edge_fn = self.edge_embedder.forward_autograd if autograd else self.edge_embedder
+        node_embed = node_fn(*args, structure_mask=structure_mask, sequence_mask=sequence_mask)
+        edge_embed = edge_fn(*args, structure_mask=structure_mask, sequence_mask=sequence_mask)
         return rotmats_1, trans_1, angles_1, seqs_1, node_embed, edge_embed
 
     def zero_center_part(self, pos, gen_mask, res_mask):
+        """flow_model.py:95-106.  CUDA tensors take the kernel (pf_zero_center); the torch formula is kept only for the
+        CPU run of the training harness (world_size-2 gloo test), which never reaches the sampling path."""
+        if pos.is_cuda and not pos.requires_grad:
+            return ops.zero_center(pos, gen_mask != 0, res_mask)
         center = torch.sum(pos * gen_mask[..., None], dim=1) / (torch.sum(gen_mask, dim=-1, keepdim=True) + 1e-8)
         center = center.unsqueeze(1)
         pos = (pos - center) * res_mask[..., None]
@@ -100,7 +108,7 @@ class FlowModel(nn.Module):
 
     @torch.no_grad()
     def sampler_init(self, batch, num_steps=100, sample_bb=True, sample_ang=True, sample_seq=True, *, noise=None,
-                     uniforms=None, seed=0, encoded=None, stream_to_host=False):
+                     uniforms=None, seed=None, encoded=None, stream_to_host=False, graph=True):
         """Everything FlowModel.sample does before its loop (flow_model.py:229-285): encode, initial noise,
         time grid, device-resident trajectory buffers.  Returns an EulerSampler whose step(n) is one loop
         iteration - bench.py times exactly that call."""
@@ -110,17 +118,22 @@ class FlowModel(nn.Module):
         enc = encoded if encoded is not None else self.encode(batch)
         if noise is None:
             noise = self.init_noise(batch, enc, sample_bb, sample_ang, sample_seq)
+        if seed is None:
+            # the categorical draws follow torch's global generator like the reference's torch.multinomial: a fresh
+            # Philox key per call, reproducible under seed_all / torch.manual_seed
+            seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64))
         return EulerSampler(self, batch, enc, noise, num_steps, (sample_bb, sample_ang, sample_seq), uniforms, seed,
-                            stream_to_host=stream_to_host)
+                            stream_to_host=stream_to_host, graph=graph)
 
     @torch.no_grad()
     def sample(self, batch, num_steps=100, sample_bb=True, sample_ang=True, sample_seq=True, *, noise=None,
-               uniforms=None, seed=0, encoded=None):
+               uniforms=None, seed=None, encoded=None, graph=True):
         """Euler sampler (flow_model.py:229-374).  Extra keyword-only hooks (all optional):
         noise: dict from init_noise() to inject the initial state; uniforms: [num_steps, 2, B, L] injected
-        U[0,1) for the two categorical draws of each step (else Philox(seed)); encoded: output of encode()."""
+        U[0,1) for the two categorical draws of each step (else Philox keyed by `seed`; None = a fresh key drawn
+        from torch's generator); encoded: output of encode(); graph: replay one captured CUDA graph per iteration."""
         smp = self.sampler_init(batch, num_steps, sample_bb, sample_ang, sample_seq, noise=noise, uniforms=uniforms,
-                                seed=seed, encoded=encoded, stream_to_host=True)
+                                seed=seed, encoded=encoded, stream_to_host=True, graph=graph)
         for n in range(num_steps):
             smp.step(n)
         return smp.trajectory_to_host()
@@ -143,7 +156,8 @@ class FlowModel(nn.Module):
         dev = batch["aa"].device
         gen_b = batch["generate_mask"]
         gen_mask, res_mask = gen_b.long(), batch["res_mask"].long()
-        rotmats_1, trans_1, angles_1, seqs_1, node_embed, edge_embed = self.encode(batch)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        rotmats_1, trans_1, angles_1, seqs_1, node_embed, edge_embed = self.encode(batch, autograd=need_grad)
         trans_1_c = trans_1
         seqs_1_simplex = self.seq_to_simplex(seqs_1)
         cfg = self._interpolant_cfg
@@ -175,7 +189,6 @@ class FlowModel(nn.Module):
             else:
                 seqs_t = seqs_1.detach().clone()
 
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if need_grad:
             pred_rotmats_1, pred_trans_1, pred_angles_1, pred_seqs_1_prob = self.ga_encoder.forward_autograd(
                 t, rotmats_t, trans_t_c, angles_t, seqs_t, node_embed, edge_embed, gen_mask, res_mask)
@@ -219,16 +232,18 @@ class FlowModel(nn.Module):
 
 class EulerSampler:
     """Device-resident state of one FlowModel.sample call.  step(n) = one iteration of the reference loop
-    (flow_model.py:287-343; the last one is :346-372): denoiser, post-processing into the trajectory slot n,
-    Euler update of the state - three C-ABI calls, no host synchronisation."""
+    (flow_model.py:287-343; the last one is :346-372) = ONE C-ABI call (pf_sampler_step: denoiser, post-processing into
+    trajectory slot n, Euler update of the state) with no host synchronisation.  The iteration counter lives on the
+    device and every argument is the same for all iterations, so the call is captured once in a CUDA graph and
+    replayed (graph=True): 73 kernel launches per iteration become one graph launch."""
 
     HOST_CHUNK = 8   # trajectory slots per device->host transfer when streaming
 
-    def __init__(self, model, batch, enc, noise, num_steps, flags, uniforms, seed, stream_to_host=False):
+    def __init__(self, model, batch, enc, noise, num_steps, flags, uniforms, seed, stream_to_host=False, graph=True):
         dev = batch["aa"].device
         B, L = batch["aa"].shape
         f32 = lambda x: x.to(torch.float32).contiguous()
-        self.model, self.num_steps, self.flags, self.seed = model, num_steps, flags, seed
+        self.model, self.num_steps, self.flags, self.seed, self.dev = model, num_steps, flags, int(seed), dev
         self.B, self.L, self.k = B, L, model.k
         self.rot1, self.tr1, self.ang1 = f32(enc[0]), f32(enc[1]), f32(enc[2])
         self.seq1 = enc[3].to(torch.int64).contiguous()
@@ -243,7 +258,8 @@ class EulerSampler:
         self.rm_f = f32(batch["res_mask"])
         self.tmask = torsions_mask.to(dev).contiguous()
         self.ts = torch.linspace(1.0e-2, 1.0, num_steps)                        # host fp32 (flow_model.py:280)
-        self.t_dev = self.ts.to(dev)[:, None].expand(num_steps, B).contiguous()  # row n: t of step n per complex
+        self.ts_dev = self.ts.to(dev)
+        self.t_dev = self.ts_dev[:, None].expand(num_steps, B).contiguous()      # row n: t of step n per complex
         if uniforms is not None:
             uniforms = f32(uniforms.to(dev))
             if uniforms.shape != (num_steps, 2, B, L):
@@ -260,6 +276,12 @@ class EulerSampler:
         self.pred = (torch.empty(B, L, 3, 3, device=dev), torch.empty(B, L, 3, device=dev),
                      torch.empty(B, L, 5, device=dev), torch.empty(B, L, 20, device=dev))
         self.gt = (self.rot1, self.tr1, self.ang1, self.seq1)
+        # device-side bookkeeping of pf_sampler_step: [next iteration, scratch]; scratch t [B]
+        self.step_dev = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.t_cur = torch.empty(B, device=dev)
+        self._next = 0
+        self.struct = self._make_struct()
+        self.use_graph, self.graph, self.launches_per_step = bool(graph), None, None
         # Streaming of the clean trajectory to pinned host memory on a side stream while the loop runs (the
         # reference blocks on nine .cpu() calls per step, flow_model.py:313-314); torch's caching host allocator
         # recycles the pinned blocks of trajectories the caller has dropped.
@@ -269,27 +291,73 @@ class EulerSampler:
             self.copy_stream = torch.cuda.Stream(device=dev)
             self._copied = 0
 
+    def _make_struct(self):
+        import ctypes
+        s = _lib.Sampler()
+        P = lambda t: t.data_ptr()
+        s.weights = ctypes.addressof(self.weights)
+        s.node_embed, s.edge_embed, s.res_mask = P(self.node_embed), P(self.edge_embed), P(self.rm_f)
+        s.workspace, s.workspace_bytes = P(self.ws), self.ws.numel()
+        s.rot1, s.trans1, s.ang1, s.seq1 = P(self.rot1), P(self.tr1), P(self.ang1), P(self.seq1)
+        s.gen_mask, s.torsions_mask = P(self.gm_u8), P(self.tmask)
+        s.trans0, s.simplex0 = P(self.tr0), P(self.sx0)
+        s.rot_t, s.trans_t, s.ang_t, s.seq_t, s.simplex_t = (P(self.rot_t), P(self.tr_t), P(self.ang_t), P(self.seq_t),
+                                                             P(self.sx_t))
+        s.pred_rot, s.pred_trans, s.pred_ang, s.logits = (P(t) for t in self.pred)
+        tj = self.traj
+        s.traj_rot, s.traj_trans, s.traj_ang, s.traj_seq, s.traj_simplex = (
+            P(tj["rotmats"]), P(tj["trans"]), P(tj["angles"]), P(tj["seqs"]), P(tj["seqs_simplex"]))
+        s.ts = P(self.ts_dev)
+        s.uniforms = P(self.uniforms) if self.uniforms is not None else None
+        s.step, s.t_cur = P(self.step_dev), P(self.t_cur)
+        s.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        s.num_steps, s.B, s.L = self.num_steps, self.B, self.L
+        s.sample_bb, s.sample_ang, s.sample_seq = (int(bool(f)) for f in self.flags)
+        s.simplex_k = float(self.k)
+        return s
+
     def _flush_to_host(self, upto):
         """Enqueue the device->host copy of trajectory slots [self._copied, upto) behind the work issued so far."""
         if self.host is None or upto <= self._copied:
             return
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
+        ev.record(torch.cuda.current_stream(self.dev))
         self.copy_stream.wait_event(ev)
         with torch.cuda.stream(self.copy_stream):
             for k, v in self.traj.items():
                 self.host[k][self._copied:upto].copy_(v[self._copied:upto], non_blocking=True)
         self._copied = upto
 
-    def step(self, n, slot=None):
-        """Loop iteration n (time ts[n]); the clean prediction goes to trajectory slot `slot` (default n)."""
-        slot = n if slot is None else slot
+    def step(self, n):
+        """Loop iteration n (time ts[n]); the clean prediction goes to trajectory slot n."""
+        if not 0 <= n < self.num_steps:
+            raise IndexError(f"iteration {n} outside [0, {self.num_steps})")
+        with torch.cuda.device(self.dev):
+            if n != self._next:                      # out-of-order call (tests, benchmarks): move the device counter
+                self.step_dev[0:1].fill_(n)
+            if self.use_graph:
+                if self.graph is None:
+                    g = torch.cuda.CUDAGraph()
+                    before = _lib.launch_count()
+                    with torch.cuda.graph(g):
+                        ops.sampler_step(self.struct, self.dev)
+                    self.graph, self.launches_per_step = g, _lib.launch_count() - before
+                self.graph.replay()
+            else:
+                ops.sampler_step(self.struct, self.dev)
+        self._next = n + 1
+        if self.host is not None and ((n + 1) % self.HOST_CHUNK == 0 or n == self.num_steps - 1):
+            self._flush_to_host(n + 1)
+
+    def step_unfused(self, n):
+        """The same iteration as three C-ABI calls with host-side bookkeeping (pf_ga_encoder_forward, pf_denoise_post,
+        pf_euler_step) - the cross-check of pf_sampler_step; not used by sample()."""
         sample_bb, sample_ang, sample_seq = self.flags
         u = self.uniforms
         ops.ga_encoder_forward(self.weights, self.t_dev[n], self.rot_t, self.tr_t, self.ang_t, self.seq_t,
                                self.node_embed, self.edge_embed, self.rm_f, self.ws, out=self.pred)
         tj = self.traj
-        clean = (tj["rotmats"][slot], tj["trans"][slot], tj["angles"][slot], tj["seqs"][slot], tj["seqs_simplex"][slot])
+        clean = (tj["rotmats"][n], tj["trans"][n], tj["angles"][n], tj["seqs"][n], tj["seqs_simplex"][n])
         ops.denoise_post(self.pred, self.gt, self.gm_u8, self.tmask, u[n, 0] if u is not None else None, self.seed,
                          2 * n, clean, self.k)
         if not sample_bb:
@@ -298,8 +366,6 @@ class EulerSampler:
             clean[2].copy_(self.ang1)
         if not sample_seq:
             clean[3].copy_(self.seq1); clean[4].copy_(self.seq1_simplex)
-        if self.host is not None and slot == n and ((n + 1) % self.HOST_CHUNK == 0 or n == self.num_steps - 1):
-            self._flush_to_host(n + 1)
         if n >= self.num_steps - 1:
             return
         d_t = float(self.ts[n + 1] - self.ts[n])

@@ -132,6 +132,15 @@ class GAEncoder(nn.Module):
             self._workspace = ws
         return ws
 
+    @torch.no_grad()
+    def seq_transformer(self, block, x, res_mask):
+        """trunk[f"seq_tfmr_{block}"](x, src_key_padding_mask=~res_mask) (ga.py:105-106) through the fused layer chains
+        and the attention kernel of the composite (pf_seq_transformer_forward) - the unit-parity seam of that module."""
+        w, _keep = self.packed_weights()
+        B, L = x.shape[:2]
+        ws = self.workspace(B, L, x.device)
+        return ops.seq_transformer_forward(w, block, x.to(torch.float32), res_mask.to(torch.float32), ws)
+
     # ------------------------------------------------------------------ training path
     def forward_autograd(self, t, rotmats_t, trans_t, angles_t, seqs_t, node_embed, edge_embed, generate_mask, res_mask):
         """Same contract as forward(), computed by differentiable torch ops over the same parameters

@@ -17,7 +17,7 @@ import torch
 from .config import load_config
 from .flow_model import FlowModel
 from .pep_dataloader import PaddingCollate, SyntheticPepDataset
-from .utils import process_dic, recursive_to, seed_all
+from .utils import load_checkpoint, process_dic, recursive_to, seed_all
 
 collate_fn = PaddingCollate(eight=False)
 
@@ -55,7 +55,7 @@ def main(argv=None):
     seed_all(114514)
     model = FlowModel(config.model).to(device)
     if args.ckpt:
-        model.load_state_dict(process_dic(torch.load(args.ckpt, map_location=device)["model"]))
+        model.load_state_dict(process_dic(load_checkpoint(args.ckpt, map_location=device)["model"]))
     model.eval()
     dataset = SyntheticPepDataset(args.num_complexes, args.pocket, args.peptide, seed=0)
     os.makedirs(os.path.join(args.output, "outputs"), exist_ok=True)

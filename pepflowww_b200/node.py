@@ -31,15 +31,26 @@ class NodeEmbedder(nn.Module):
                 l6.weight.t().contiguous(), l6.bias)
 
     def forward(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask=None, sequence_mask=None):
+        """The fused kernel (pf_node_embed).  CUDA tensors, no autograd - no silent torch or CPU fallback; the
+        differentiable formulation of the training path is forward_autograd()."""
+        if not pos_atoms.is_cuda:
+            raise RuntimeError("NodeEmbedder.forward runs the CUDA kernel (no CPU fallback); got a CPU tensor")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("NodeEmbedder.forward runs the inference kernel; wrap the call in torch.no_grad() "
+                               "(the autograd training path is NodeEmbedder.forward_autograd)")
+        if not (self.max_num_atoms == 15 and self.max_aa_types == 22 and self.feat_dim == 128 and
+                self.dihed_embed.num_funcs == 3 and pos_atoms.shape[2] >= 15):
+            raise ValueError("pf_node_embed is specialised to 15 atoms / 22 residue types / 128 channels")
+        from . import ops
+        if sequence_mask is not None:
+            aa = torch.where(sequence_mask, aa, torch.full_like(aa, fill_value=int(AA.UNK)))
+        return ops.node_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, self._kernel_constants())
+
+    def forward_autograd(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask=None, sequence_mask=None):
+        """Same contract in differentiable torch ops over the same parameters (models_con/node.py:35-105): the gradient
+        path of FlowModel.forward / train_ddp.py."""
         N, L = aa.size()
         A = self.max_num_atoms
-        fused = (pos_atoms.is_cuda and not torch.is_grad_enabled() and A == 15 and self.max_aa_types == 22 and
-                 self.feat_dim == 128 and self.dihed_embed.num_funcs == 3 and pos_atoms.shape[2] >= 15)
-        if fused:
-            from . import ops
-            if sequence_mask is not None:
-                aa = torch.where(sequence_mask, aa, torch.full_like(aa, fill_value=int(AA.UNK)))
-            return ops.node_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, self._kernel_constants())
         mask_residue = mask_atoms[:, :, BBHeavyAtom.CA]
         pos_atoms, mask_atoms = pos_atoms[:, :, :A], mask_atoms[:, :, :A]
         if sequence_mask is not None:

@@ -220,6 +220,35 @@ def ga_encoder_forward(weights_struct, t, rot_t, trans_t, angles_t, seqs_t, node
     return out
 
 
+def seq_transformer_forward(weights_struct, block, x, res_mask, workspace):
+    """The two post-norm encoder layers of block `block` (ga.py:105-106) through the composite's own kernels."""
+    import ctypes
+    lib = _lib.lib_for(x.device)
+    B, L = x.shape[:2]
+    y = torch.empty(B, L, 128, device=x.device, dtype=F32)
+    check(lib.pf_seq_transformer_forward(ctypes.addressof(weights_struct), int(block), ptr(_c(x)), ptr(_c(res_mask)),
+                                         ptr(y), ptr(workspace, U8), workspace.numel(), B, L, stream(x.device)))
+    return y
+
+
+def zero_center(pos, gen_mask, res_mask):
+    """FlowModel.zero_center_part (flow_model.py:95-106) as one kernel: returns (centered * res_mask, center [B,1,3])."""
+    lib = _lib.lib_for(pos.device)
+    B, L = pos.shape[:2]
+    out = _c(pos).clone()
+    center = torch.empty(B, 1, 3, device=pos.device, dtype=F32)
+    check(lib.pf_zero_center(ptr(out), ptr(_c(gen_mask, torch.bool).view(U8), U8), ptr(_c(res_mask)), ptr(center), B, L,
+                             stream(pos.device)))
+    return out, center
+
+
+def sampler_step(sampler_struct, device):
+    """One iteration of the FlowModel.sample loop (pf_sampler_step): denoiser + post-processing + Euler update."""
+    import ctypes
+    lib = _lib.lib_for(device)
+    check(lib.pf_sampler_step(ctypes.addressof(sampler_struct), stream(device)))
+
+
 def edge_embed(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, consts):
     """EdgeEmbedder.forward (models_con/edge.py:39-112) as one fused kernel (pf_edge_embed).  `consts` is the tuple of
     host-prepared constants in the order of the C prototype (EdgeEmbedder._kernel_constants)."""

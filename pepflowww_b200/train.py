@@ -81,7 +81,11 @@ def make_loader(dataset, batch_size, rank=0, world=1, num_workers=0, seed=0):
 
 
 def checkpoint_dict(config, model, optimizer, scheduler, iteration):
-    return {"config": config, "model": model.state_dict(), "optimizer": optimizer.state_dict(),
+    """train_ddp.py:206-212: `model` is what the training loop holds (the DDP wrapper when distributed, so its keys carry
+    the `module.` prefix exactly like the reference's checkpoints; utils.process_dic strips it on load); `iteration` is
+    the last completed iteration; the config goes in as plain dicts so the file loads without this package."""
+    from .utils import plain_config
+    return {"config": plain_config(config), "model": model.state_dict(), "optimizer": optimizer.state_dict(),
             "scheduler": scheduler.state_dict(), "iteration": iteration}
 
 
@@ -119,9 +123,10 @@ def main(argv=None):
     bs = args.batch_size or config.train.batch_size
     it_first = 1
     if args.resume:                                     # train_ddp.py:105-114
-        ckpt = torch.load(args.resume, map_location=dev, weights_only=False)
-        it_first = ckpt["iteration"]
-        net.load_state_dict(ckpt["model"])
+        from .utils import load_checkpoint, process_dic
+        ckpt = load_checkpoint(args.resume, map_location=dev)
+        it_first = ckpt["iteration"] + 1                # the checkpoint holds the last completed iteration
+        net.load_state_dict(process_dic(ckpt["model"]))  # reference checkpoints come from the DDP wrapper ('module.')
         optimizer.load_state_dict(ckpt["optimizer"])
         scheduler.load_state_dict(ckpt["scheduler"])
     dataset = SyntheticPepDataset(args.dataset_size, args.pocket, args.peptide, seed=0)
@@ -143,8 +148,8 @@ def main(argv=None):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         if args.save:
-            torch.save(checkpoint_dict(config, model.module if world > 1 else model, optimizer, scheduler,
-                                       it_first + args.warmup + args.iters), args.save)
+            torch.save(checkpoint_dict(config, model, optimizer, scheduler, it_first + args.warmup + args.iters - 1),
+                       args.save)
         print(json.dumps({"metric": "training samples/sec (flow-matching loss, fwd+bwd+Adam)", "unit": "samples/s",
                           "value": bs * world / (float(ms) / 1e3), "ms_per_iter": float(ms), "n_gpus": world,
                           "batch_per_gpu": bs, "residues": args.pocket + args.peptide, "loss": float(last[0]),

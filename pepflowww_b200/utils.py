@@ -19,6 +19,37 @@ def process_dic(state_dict):
     return out
 
 
+def load_checkpoint(path, map_location="cpu"):
+    """torch.load of a training checkpoint {config, model, optimizer, scheduler, iteration} (train_ddp.py:206-212;
+    loaded at inference.py:61-65).  The reference pickles its config as easydict.EasyDict; easydict is not in this
+    image, so a stand-in module whose EasyDict is config.AttrDict is registered for the duration of the load.
+    weights_only=False: the config object is not a tensor (torch >= 2.6 defaults to weights_only=True and would reject
+    it) - only load checkpoints you trust, as with the reference."""
+    import sys
+    import types
+
+    from .config import AttrDict
+    shim = None
+    if "easydict" not in sys.modules:
+        shim = types.ModuleType("easydict")
+        shim.EasyDict = AttrDict
+        sys.modules["easydict"] = shim
+    try:
+        return torch.load(path, map_location=map_location, weights_only=False)
+    finally:
+        if shim is not None:
+            sys.modules.pop("easydict", None)
+
+
+def plain_config(obj):
+    """Nested AttrDict / EasyDict -> plain dict / list (what checkpoint_dict stores: loadable without this package)."""
+    if isinstance(obj, dict):
+        return {k: plain_config(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(plain_config(v) for v in obj)
+    return obj
+
+
 def recursive_to(obj, device):
     if isinstance(obj, torch.Tensor):
         return obj.to(device, non_blocking=True)

@@ -26,7 +26,7 @@ int main(int argc, char** argv) {
   size_t (*p_pf_ga_encoder_workspace_bytes)(int, int);
   BIND(pf_version) BIND(pf_strerror) BIND(pf_check_config) BIND(pf_so3_log) BIND(pf_full_atom_reconstruction)
   BIND(pf_torsion_angles) BIND(pf_ga_encoder_workspace_bytes)
-  if (p_pf_version() != 3) return 3;
+  if (p_pf_version() != 4) return 3;
   if (strcmp(p_pf_strerror(PF_OK), "ok") != 0 || !strlen(p_pf_strerror(PF_ERR_NULL_POINTER))) return 4;
   if (p_pf_check_config(128, 64, 128, 8, 8, 12, 4, 2) != PF_OK) return 5;
   if (p_pf_check_config(256, 64, 128, 8, 8, 12, 4, 2) != PF_ERR_BAD_CONFIG) return 6;

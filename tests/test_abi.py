@@ -29,7 +29,7 @@ def test_header_symbols_exported_and_bound():
 def test_version_strerror_and_config_check():
     from pepflowww_b200 import _lib
     lib = _lib.load()
-    assert lib.pf_version() == 3
+    assert lib.pf_version() == 4
     assert lib.pf_strerror(0) == b"ok"
     assert b"shape" in lib.pf_strerror(-1)
     assert lib.pf_check_config(128, 64, 128, 8, 8, 12, 4, 2) == 0

@@ -477,7 +477,9 @@ def test_node_embed_kernel(dev, model, state_dict):
     with torch.no_grad():
         fused = model.node_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx)
     with torch.enable_grad():
-        torch_path = model.node_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx).detach()
+        torch_path = model.node_embedder.forward_autograd(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx).detach()
+        with pytest.raises(RuntimeError, match="forward_autograd"):       # no silent dispatch on the grad mode
+            model.node_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx)
     e_big = rel_err(fused, torch_path)
     print("node_embed kernel: golden %.2e padded %.2e no-mask %.2e L=271 vs torch ops %.2e" % (e_gold, e_pad, e_nomask, e_big))
     assert max(e_gold, e_pad, e_nomask, e_big) < TOL
@@ -531,8 +533,10 @@ def test_edge_embed_kernel(dev, model, state_dict):
     ctx = big["mask_heavyatom"][:, :, 1] & ~big["generate_mask"]
     with torch.no_grad():
         fused = model.edge_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx)
-    with torch.enable_grad():                                          # autograd on: the torch formulation runs
-        torch_path = model.edge_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx).detach()
+    with torch.enable_grad():                                          # the explicit torch formulation of the training path
+        torch_path = model.edge_embedder.forward_autograd(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx).detach()
+        with pytest.raises(RuntimeError, match="forward_autograd"):
+            model.edge_embedder(*[big[k] for k in keys], structure_mask=ctx, sequence_mask=ctx)
     res["L=271 vs torch ops"] = errs(fused, torch_path, big["pos_heavyatom"])
     print("edge_embed kernel (well-conditioned pairs, all pairs, share well-conditioned): " +
           "; ".join("%s %.2e %.2e %.2f" % ((k,) + v) for k, v in res.items()))

@@ -1,0 +1,340 @@
+"""GPU parity, round 2: the headline residue count (256 + 15) against the CPU oracle, the encode -> denoiser composition,
+the transformer seam, the one-call / graph-replayed sampler iteration, and statistical checks of the Philox draws.
+
+Error norms: rel_err = max|a - b| / max|b| over the tensor; translations additionally get a
+PER-RESIDUE bound |dx_i|_inf <= 1e-4 * max(|x_i|_inf, 1 A) so that a large coordinate somewhere cannot hide an error
+elsewhere; angles are compared on the circle; residue types exactly.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pepflow_oracle as orc
+from tests.conftest import circ_err, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+GA_KEYS = ("t", "rotmats_t", "trans_t", "angles_t", "seqs_t", "node_embed", "edge_embed", "generate_mask", "res_mask")
+BATCH_KEYS = ("aa", "pos_heavyatom", "mask_heavyatom", "res_nb", "chain_nb", "generate_mask", "res_mask", "torsion_angle",
+              "torsion_angle_mask")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def model(dev, state_dict):
+    from pepflowww_b200.config import load_config
+    from pepflowww_b200.flow_model import FlowModel
+    cfg, _ = load_config()
+    m = FlowModel(cfg.model).eval()
+    m.load_state_dict(state_dict)
+    return m.to(dev)
+
+
+def per_residue_trans_err(x, ref):
+    """max_i |dx_i|_inf / max(|x_i|_inf, 1)"""
+    d = (x.double() - ref.double()).abs().amax(-1)
+    return float((d / ref.double().abs().amax(-1).clamp(min=1.0)).max())
+
+
+def make_noise(enc, gm, g):
+    B, L = gm.shape
+    noise = {"rotmats_0": orc.quat_to_rot(torch.nn.functional.normalize(torch.randn(B, L, 4, generator=g), dim=-1)),
+             "trans_0": torch.randn(B, L, 3, generator=g), "angles_0": torch.rand(B, L, 5, generator=g) * 2 * math.pi,
+             "seqs_0": torch.randint(0, 20, (B, L), generator=g), "seqs_0_simplex": 5 * torch.randn(B, L, 20, generator=g)}
+    noise["rotmats_0"] = torch.where(gm[..., None, None], noise["rotmats_0"], enc["rotmats_1"])
+    noise["trans_0"] = torch.where(gm[..., None], noise["trans_0"], enc["trans_1"])
+    noise["angles_0"] = torch.where(gm[..., None], noise["angles_0"], enc["angles_1"])
+    noise["seqs_0"] = torch.where(gm, noise["seqs_0"], enc["seqs_1"])
+    noise["seqs_0_simplex"] = torch.where(gm[..., None], noise["seqs_0_simplex"], orc.seq_to_simplex(enc["seqs_1"]))
+    return noise
+
+
+@pytest.fixture(scope="module")
+def headline(state_dict):
+    """Two synthetic complexes of 256 + 15 residues, the oracle's encoder outputs and a denoiser input on them."""
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    batch = synthetic_batch(2, 256, 15, seed=21)
+    enc = orc.encode(state_dict, batch)
+    B, L = batch["aa"].shape
+    rng = np.random.default_rng(8)
+    q = torch.from_numpy(rng.standard_normal((B, L, 4))).float()
+    gm = batch["generate_mask"]
+    inp = dict(t=torch.tensor([[0.21], [0.68]]),
+               rotmats_t=torch.where(gm[..., None, None], orc.quat_to_rot(q / q.norm(dim=-1, keepdim=True)), enc["rotmats_1"]),
+               trans_t=enc["trans_1"] + gm[..., None] * torch.from_numpy(rng.standard_normal((B, L, 3))).float(),
+               angles_t=torch.from_numpy(rng.uniform(0, 2 * math.pi, (B, L, 5))).float(),
+               seqs_t=torch.from_numpy(rng.integers(0, 20, (B, L))), node_embed=enc["node_embed"],
+               edge_embed=enc["edge_embed"], generate_mask=gm.long(), res_mask=batch["res_mask"].long())
+    return batch, enc, inp
+
+
+# ------------------------------------------------------------------------------------------------ cfg4 residue count
+def test_ga_encoder_vs_oracle_headline_shape(dev, model, state_dict, headline):
+    """GAEncoder.forward at L = 271 (default kernel variants) against the oracle (models_con/ga.py:87-127)."""
+    _, _, inp = headline
+    trace = []
+    ref = orc.ga_encoder_forward(state_dict, *[inp[k] for k in GA_KEYS], trace=trace)
+    with torch.no_grad():
+        out = model.ga_encoder(*[inp[k].to(dev) for k in GA_KEYS])
+    errs = dict(rot=rel_err(out[0].cpu(), ref[0]), trans=rel_err(out[1].cpu(), ref[1]),
+                trans_res=per_residue_trans_err(out[1].cpu(), ref[1]), ang=circ_err(out[2].cpu(), ref[2]),
+                logits=rel_err(out[3].cpu(), ref[3]))
+    print("L=271 denoiser vs oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["rot"] < TOL and errs["trans"] < TOL and errs["trans_res"] < TOL
+    assert errs["ang"] < TOL * 2 * math.pi and errs["logits"] < TOL
+    assert torch.equal(out[3].cpu().argmax(-1), ref[3].argmax(-1))
+
+
+def test_module_seams_headline_shape(dev, model, state_dict, headline):
+    """ipa_1 and edge_transition_1 at L = 271 against the oracle (ipa_pytorch.py:316-484, :233-248): the pair-bias /
+    o_pair path that an SE(3)-equivariance test cannot see."""
+    from pepflowww_b200.rigid import create_rigid
+    _, enc, inp = headline
+    g = torch.Generator().manual_seed(3)
+    B, L = inp["seqs_t"].shape
+    s = torch.randn(B, L, 128, generator=g)
+    z = enc["edge_embed"]
+    m = torch.ones(B, L)
+    m[1, 200:230] = 0.0
+    p = "ga_encoder.trunk."
+    fr = orc.Frames(inp["trans_t"], rot=inp["rotmats_t"])
+    ref_ipa = orc.ipa_forward(state_dict, p + "ipa_1.", s, z, fr, m)
+    ref_et = orc.edge_transition(state_dict, p + "edge_transition_1.", s, z)
+    rig = create_rigid(inp["rotmats_t"].to(dev), inp["trans_t"].to(dev))
+    with torch.no_grad():
+        ipa = model.ga_encoder.trunk["ipa_1"](s.to(dev), z.to(dev), rig, m.to(dev))
+        et = model.ga_encoder.trunk["edge_transition_1"](s.to(dev), z.to(dev))
+    valid = m.bool()
+    e_ipa, e_et = rel_err(ipa.cpu()[valid], ref_ipa[valid]), rel_err(et.cpu(), ref_et)
+    print(f"L=271 seams vs oracle: ipa_1 {e_ipa:.2e} edge_transition_1 {e_et:.2e}")
+    assert e_ipa < TOL and e_et < TOL
+
+
+def test_seq_transformer_seam_golden(dev, model):
+    """seq_tfmr_0 (torch.nn.TransformerEncoder, ga.py:53-62,105-106) through the composite's fused chains against the
+    reference's own output `tf0`, padded and unpadded batch."""
+    for tag in ("ga_encoder_a", "ga_encoder_b"):
+        g = load_golden(tag)
+        m = g["res_mask"].float()
+        s = (g["node_embed"] * m[..., None]).to(dev)
+        y = model.ga_encoder.seq_transformer(0, s, m.to(dev))
+        valid = g["res_mask"].bool()
+        assert rel_err(y.cpu()[valid], g["tf0"][valid]) < TOL, tag
+
+
+# ------------------------------------------------------------------------------------------------ encode -> denoiser
+def test_sample_step0_through_own_encode_golden(dev, model):
+    """FlowModel.sample with the repo's OWN encode (edge_embed / node_embed kernels feeding the denoiser) against the
+    reference's recorded 4-step run: step 0 within 1e-4, exact residue types."""
+    g, s = load_golden("encode"), load_golden("sample")
+    batch = {k: g[k].to(dev) for k in BATCH_KEYS}
+    noise = {k: s[k].to(dev) for k in ("rotmats_0", "trans_0", "angles_0", "seqs_0", "seqs_0_simplex")}
+    B, L = g["aa"].shape
+    uni = s["uniforms"][1:].reshape(4, 2, B, L)
+    traj = model.sample(batch, num_steps=4, noise=noise, uniforms=uni)
+    assert torch.equal(traj[0]["seqs"], s["step0_seqs"])
+    errs = (rel_err(traj[0]["rotmats"], s["step0_rotmats"]), rel_err(traj[0]["trans"], s["step0_trans"]),
+            per_residue_trans_err(traj[0]["trans"], s["step0_trans"]), circ_err(traj[0]["angles"], s["step0_angles"]))
+    print("own encode -> step 0 vs reference golden:", ["%.2e" % e for e in errs])
+    assert errs[0] < TOL and errs[1] < TOL and errs[2] < TOL and errs[3] < TOL * 2 * math.pi
+
+
+def test_sample_through_own_encode_headline_shape(dev, model, state_dict, headline):
+    """256 + 15 residues: own encode + two sampler iterations against orc.encode + orc.sample_loop with the same
+    injected noise and uniforms; the second step is teacher-forced from the oracle's state."""
+    from pepflowww_b200.constants import torsions_mask
+    batch, enc, _ = headline
+    B, L = batch["aa"].shape
+    g = torch.Generator().manual_seed(17)
+    gm = batch["generate_mask"]
+    noise = make_noise(enc, gm, g)
+    steps = 2
+    uni = torch.rand(steps, 2, B, L, generator=g)
+    ref = orc.sample_loop(state_dict, enc, noise, uni, gm, batch["res_mask"], steps, torsions_mask)
+    dbatch = {k: batch[k].to(dev) for k in BATCH_KEYS}
+    smp = model.sampler_init(dbatch, num_steps=steps, noise={k: v.to(dev) for k, v in noise.items()}, uniforms=uni)
+    # the embedders against the oracle at this size (acos() conditioning: see test_edge_embed_kernel)
+    print("own encode vs oracle: node %.2e edge %.2e" % (rel_err(smp.node_embed.cpu(), enc["node_embed"]),
+                                                         rel_err(smp.edge_embed.cpu(), enc["edge_embed"])))
+    state = (noise["rotmats_0"], noise["trans_0"], noise["angles_0"], noise["seqs_0"], noise["seqs_0_simplex"])
+    gt = (enc["rotmats_1"], enc["trans_1"], enc["angles_1"], enc["seqs_1"])
+    ts = torch.linspace(1e-2, 1.0, steps)
+    for n in range(steps):
+        smp.rot_t.copy_(state[0]); smp.tr_t.copy_(state[1]); smp.ang_t.copy_(state[2])
+        smp.seq_t.copy_(state[3]); smp.sx_t.copy_(state[4])
+        smp.step(n)
+        got = {k: v[n].cpu() for k, v in smp.traj.items()}
+        errs = (rel_err(got["rotmats"], ref[n]["rotmats"]), rel_err(got["trans"], ref[n]["trans"]),
+                per_residue_trans_err(got["trans"], ref[n]["trans"]), circ_err(got["angles"], ref[n]["angles"]))
+        print(f"L=271 sample step {n} (own encode) vs oracle:", ["%.2e" % e for e in errs])
+        assert torch.equal(got["seqs"], ref[n]["seqs"]), n
+        assert errs[0] < TOL and errs[1] < TOL and errs[2] < TOL and errs[3] < TOL * 2 * math.pi, n
+        if n + 1 < steps:
+            clean = (ref[n]["rotmats"], ref[n]["trans"], ref[n]["angles"], ref[n]["seqs"])
+            state = orc.euler_update(state, clean, gt, (noise["trans_0"], noise["seqs_0_simplex"]), gm, ts[n + 1] - ts[n],
+                                     uni[n, 1], torsions_mask)
+
+
+# ------------------------------------------------------------------------------------------------ sampler iteration
+@pytest.mark.parametrize("flags", [(True, True, True), (False, True, True), (True, False, True), (True, True, False)])
+@pytest.mark.parametrize("inject", [True, False])
+def test_sampler_step_graph_fused_unfused_identical(dev, model, flags, inject):
+    """pf_sampler_step replayed from a CUDA graph == the same call launched directly == the three-call iteration
+    (pf_ga_encoder_forward + pf_denoise_post + pf_euler_step) with host bookkeeping: bit-identical trajectories and
+    states, for every sample_bb / sample_ang / sample_seq combination the reference's loop has (flow_model.py:306-342)."""
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in synthetic_batch(3, 20, 5, seed=2).items()}
+    steps = 5
+    B, L = batch["aa"].shape
+    with torch.no_grad():
+        enc = model.encode(batch)
+    torch.manual_seed(11)
+    noise = model.init_noise(batch, enc, *flags)
+    uni = torch.rand(steps, 2, B, L, generator=torch.Generator().manual_seed(4)) if inject else None
+    runs = []
+    for mode in ("graph", "direct", "unfused"):
+        smp = model.sampler_init(batch, steps, *flags, noise=noise, uniforms=uni, seed=77, encoded=enc,
+                                 graph=(mode == "graph"))
+        for n in range(steps):
+            (smp.step_unfused if mode == "unfused" else smp.step)(n)
+        torch.cuda.synchronize()
+        runs.append(({k: v.clone() for k, v in smp.traj.items()},
+                     [t.clone() for t in (smp.rot_t, smp.tr_t, smp.ang_t, smp.seq_t, smp.sx_t)]))
+        if mode == "graph":
+            assert smp.graph is not None and int(smp.step_dev[0]) == steps
+    for other in runs[1:]:
+        for k in runs[0][0]:
+            assert torch.equal(runs[0][0][k], other[0][k]), k
+        for a, b in zip(runs[0][1], other[1]):
+            assert torch.equal(a, b)
+    # pinned modalities equal the ground truth in every slot
+    tj = runs[0][0]
+    gen = batch["generate_mask"]
+    if not flags[0]:
+        assert torch.equal(tj["rotmats"][-1], enc[0]) and torch.equal(tj["trans"][-1], enc[1])
+    if not flags[1]:
+        assert torch.equal(tj["angles"][-1], enc[2])
+    if not flags[2]:
+        assert torch.equal(tj["seqs"][-1], enc[3])
+    assert torch.equal(tj["trans"][-1][~gen], enc[1][~gen])
+
+
+def test_sample_seed_controls_draws(dev, model):
+    """the categorical draws follow torch's generator unless a seed is given (no fixed default stream)."""
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in synthetic_batch(4, 16, 8, seed=6).items()}
+    with torch.no_grad():
+        enc = model.encode(batch)
+    torch.manual_seed(5)
+    noise = model.init_noise(batch, enc)
+    kw = dict(num_steps=3, noise=noise, encoded=enc)
+    torch.manual_seed(100)
+    sa = model.sampler_init(batch, **kw)
+    sb = model.sampler_init(batch, **kw)                # same call again: a fresh Philox key
+    torch.manual_seed(100)
+    sc = model.sampler_init(batch, **kw)                # re-seeded: the same key as the first call
+    assert sa.seed == sc.seed and sa.seed != sb.seed
+    torch.manual_seed(100)
+    a = model.sample(batch, **kw)
+    torch.manual_seed(100)
+    c = model.sample(batch, **kw)
+    assert torch.equal(a[-1]["seqs"], c[-1]["seqs"]) and torch.equal(a[-1]["rotmats"], c[-1]["rotmats"])
+    d = model.sample(batch, seed=9, **kw)
+    e = model.sample(batch, seed=9, **kw)
+    assert torch.equal(d[-1]["seqs"], e[-1]["seqs"]) and torch.equal(d[-1]["angles"], e[-1]["angles"])
+
+
+def test_zero_center_kernel(dev):
+    """FlowModel.zero_center_part (flow_model.py:95-106) as a kernel against the oracle, ragged masks included."""
+    from pepflowww_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for B, L in ((1, 1), (3, 37), (64, 271), (2, 600)):
+        pos = torch.randn(B, L, 3, generator=g) * 10
+        gen = torch.rand(B, L, generator=g) > 0.7
+        gen[0] = False                                   # empty generate mask: centre 0 / 1e-8 -> 0
+        rm = torch.rand(B, L, generator=g) > 0.1
+        ref, cref = orc.zero_center_part(pos, gen, rm)
+        out, c = ops.zero_center(pos.to(dev), gen.to(dev), rm.to(dev))
+        assert float((out.cpu() - ref).abs().max()) < 2e-5, (B, L)
+        assert float((c.cpu() - cref).abs().max()) < 2e-5, (B, L)
+
+
+def test_philox_categorical_frequencies(dev):
+    """The Philox-driven categorical draw (sample_from, layers.py:17-22): frequencies over 200k draws match
+    softmax(logits) (chi-square), different counters give independent streams, uniforms are in [0, 1)."""
+    from pepflowww_b200 import ops
+    from pepflowww_b200.constants import torsions_mask
+    n = 200_000
+    g = torch.Generator().manual_seed(1)
+    logits_row = torch.randn(20, generator=g) * 1.5
+    p = torch.softmax(logits_row, -1).double()
+    D = lambda t: t.to(dev).contiguous()
+    eye = torch.eye(3).expand(1, n, 3, 3)
+    pred = (D(eye), D(torch.zeros(1, n, 3)), D(torch.zeros(1, n, 5)), D(logits_row.expand(1, n, 20)))
+    gt = (D(eye), D(torch.zeros(1, n, 3)), D(torch.zeros(1, n, 5)), D(torch.zeros(1, n, dtype=torch.int64)))
+    gm = D(torch.ones(1, n, dtype=torch.uint8))
+    clean = (torch.empty(1, n, 3, 3, device=dev), torch.empty(1, n, 3, device=dev), torch.empty(1, n, 5, device=dev),
+             torch.empty(1, n, dtype=torch.int64, device=dev), torch.empty(1, n, 20, device=dev))
+    draws = []
+    for counter in (0, 1):
+        ops.denoise_post(pred, gt, gm, D(torsions_mask), None, 1234, counter, clean, 5.0)
+        draws.append(clean[3].cpu().reshape(-1).clone())
+    for d in draws:
+        assert int(d.min()) >= 0 and int(d.max()) <= 19
+        obs = torch.bincount(d, minlength=20).double()
+        chi2 = float(((obs - n * p) ** 2 / (n * p)).sum())
+        assert chi2 < 60.0, chi2                         # 19 dof: P(chi2 > 60) ~ 4e-6
+    # independence of the two counters: joint table of (draw0 == k0, draw1 == k0) for the most likely class
+    k0 = int(p.argmax())
+    a, b = (draws[0] == k0).double(), (draws[1] == k0).double()
+    corr = float(((a - a.mean()) * (b - b.mean())).mean() / (a.std() * b.std()))
+    assert abs(corr) < 0.01, corr
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_sample_equals_single_gpu(state_dict):
+    """SURVEY section 4 tier 4 / section 8e: complexes sharded over two devices (injected noise and uniforms) give
+    bit-for-bit the single-device trajectory - there is no data-path collective to perturb anything."""
+    from pepflowww_b200.config import load_config
+    from pepflowww_b200.dist_utils import shard_range
+    from pepflowww_b200.flow_model import FlowModel
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    from pepflowww_b200.utils import recursive_to
+    cfg, _ = load_config()
+    B, steps = 6, 4
+    host = synthetic_batch(B, 40, 8, seed=13)
+    L = host["aa"].shape[1]
+    g = torch.Generator().manual_seed(2)
+    uni = torch.rand(steps, 2, B, L, generator=g)
+    models = []
+    for d in range(2):
+        m = FlowModel(cfg.model).eval()
+        m.load_state_dict(state_dict)
+        models.append(m.to(torch.device("cuda", d)))
+    with torch.cuda.device(0):
+        b0 = recursive_to(host, torch.device("cuda", 0))
+        with torch.no_grad():
+            enc0 = models[0].encode(b0)
+        torch.manual_seed(3)
+        noise = models[0].init_noise(b0, enc0)
+        full = models[0].sample(b0, num_steps=steps, noise=noise, uniforms=uni)
+    parts = []
+    for r in range(2):
+        lo, hi = shard_range(B, r, 2)
+        dev = torch.device("cuda", r)
+        with torch.cuda.device(r):
+            shard = {k: (v[lo:hi] if isinstance(v, torch.Tensor) else v[lo:hi]) for k, v in host.items()}
+            parts.append(models[r].sample(recursive_to(shard, dev), num_steps=steps,
+                                          noise={k: v[lo:hi].to(dev) for k, v in noise.items()},
+                                          uniforms=uni[:, :, lo:hi]))
+    for n in range(steps):
+        for k in full[n]:
+            assert torch.equal(torch.cat([parts[0][n][k], parts[1][n][k]], 0), full[n][k]), (n, k)

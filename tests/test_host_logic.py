@@ -34,9 +34,11 @@ def test_embedders_match_reference_golden(state_dict):
     batch = {k: g[k] for k in ("aa", "pos_heavyatom", "mask_heavyatom", "res_nb", "chain_nb", "generate_mask",
                                "res_mask", "torsion_angle", "torsion_angle_mask")}
     with torch.no_grad():
-        r1, x1, a1, s1, node, edge = model.encode(batch)
+        r1, x1, a1, s1, node, edge = model.encode(batch, autograd=True)   # the torch formulations (training path) on CPU
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            model.encode(batch)                        # the kernel path refuses CPU tensors instead of falling back
         model.edge_embedder.chunk_bytes = 1 << 16      # force the row-chunked path too
-        edge_chunked = model.edge_embedder(batch["aa"], batch["res_nb"], batch["chain_nb"], batch["pos_heavyatom"],
+        edge_chunked = model.edge_embedder.forward_autograd(batch["aa"], batch["res_nb"], batch["chain_nb"], batch["pos_heavyatom"],
                                            batch["mask_heavyatom"], structure_mask=~batch["generate_mask"],
                                            sequence_mask=~batch["generate_mask"])
     assert rel_err(r1, g["rotmats_1"]) < 1e-6
@@ -265,3 +267,96 @@ def test_padding_collate_matches_reference():
             else:
                 assert b[k].dtype == v.dtype and torch.equal(b[k], v), k
     assert PaddingCollate(no_padding={"resseq"}).no_padding == {"resseq"}
+
+
+def test_benchdata_generators_equal_the_products(state_dict):
+    """bench.py's reference arm builds its workload from benchdata/ (no product import): same complexes, same weights."""
+    import benchdata
+    from pepflowww_b200.constants import restype_to_heavyatom_masks, torsions_mask
+    from pepflowww_b200.pep_dataloader import synthetic_batch
+    a = benchdata.synthetic_batch(3, 20, 5, seed=2, first_index=4)
+    b = synthetic_batch(3, 20, 5, seed=2, first_index=4)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    sd = benchdata.reference_state_dict(114514)
+    assert set(sd) == set(state_dict)
+    for k in sd:
+        assert torch.equal(sd[k], state_dict[k]), k
+    assert torch.equal(benchdata.torsions_mask, torsions_mask)
+    from benchdata.synthetic import restype_to_heavyatom_masks as hm
+    assert torch.equal(hm, restype_to_heavyatom_masks)
+
+
+def test_checkpoint_round_trip_and_reference_style_checkpoint(tmp_path, state_dict):
+    """ADVICE r1: train -> save -> load must work on torch >= 2.6 (weights_only default) and a checkpoint written by the
+    reference's DDP loop ('module.' keys, config pickled as easydict.EasyDict, iteration = last completed) must load."""
+    import pickle
+    import sys
+    import types
+
+    from pepflowww_b200.config import load_config
+    from pepflowww_b200.flow_model import FlowModel
+    from pepflowww_b200.train import checkpoint_dict, get_optimizer, get_scheduler
+    from pepflowww_b200.utils import load_checkpoint, process_dic
+    cfg, _ = load_config()
+    net = FlowModel(cfg.model)
+    net.load_state_dict(state_dict)
+    opt = get_optimizer(cfg.train.optimizer, net)
+    sch = get_scheduler(cfg.train.scheduler, opt)
+    path = str(tmp_path / "ckpt.pt")
+    torch.save(checkpoint_dict(cfg, net, opt, sch, 41), path)
+    ck = load_checkpoint(path)
+    assert ck["iteration"] == 41 and type(ck["config"]) is dict and ck["config"]["train"]["batch_size"] == cfg.train.batch_size
+    net2 = FlowModel(cfg.model)
+    net2.load_state_dict(process_dic(ck["model"]))
+    for k, v in net2.state_dict().items():
+        assert torch.equal(v, state_dict[k]), k
+    # the same file also loads with plain torch.load defaults minus the config (tensors + containers only)
+    assert torch.load(path, weights_only=True)["iteration"] == 41
+
+    # reference-style: EasyDict config from a module this image does not have, DDP-prefixed keys
+    fake = types.ModuleType("easydict")
+
+    class EasyDict(dict):
+        pass
+
+    EasyDict.__module__, EasyDict.__qualname__ = "easydict", "EasyDict"
+    fake.EasyDict = EasyDict
+    sys.modules["easydict"] = fake
+    try:
+        ref_path = str(tmp_path / "model1.pt")
+        torch.save({"config": EasyDict(model=EasyDict(encoder=1)), "model": {"module." + k: v for k, v in state_dict.items()},
+                    "optimizer": {}, "scheduler": {}, "iteration": 7}, ref_path, pickle_protocol=pickle.DEFAULT_PROTOCOL)
+    finally:
+        del sys.modules["easydict"]
+    assert "easydict" not in sys.modules
+    ck = load_checkpoint(ref_path)
+    assert ck["config"].model.encoder == 1 and ck["iteration"] == 7
+    net3 = FlowModel(cfg.model)
+    net3.load_state_dict(process_dic(ck["model"]))
+    assert "easydict" not in sys.modules
+
+
+def test_reference_arm_does_not_import_the_product(tmp_path):
+    """VERDICT r1 weak #11: `bench.py --impl reference` must not import pepflowww_b200 nor map libpepflow_b200.so."""
+    import subprocess
+    import sys
+
+    from tests.conftest import ROOT
+    code = (
+        "import runpy, sys\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--cpu-batch', '1', '--pocket', '12', '--peptide', '4']\n"
+        "try:\n"
+        "    runpy.run_path('bench.py', run_name='__main__')\n"
+        "except SystemExit:\n"
+        "    pass\n"
+        "bad = [m for m in sys.modules if m.startswith('pepflowww_b200')]\n"
+        "assert not bad, bad\n"
+        "assert 'libpepflow' not in open('/proc/self/maps').read()\n"
+        "print('REFERENCE_ARM_CLEAN')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "REFERENCE_ARM_CLEAN" in r.stdout
+    import json
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["gpu_launches"] == 0
