@@ -51,21 +51,20 @@ int pf_check_config(int c_s, int c_z, int c_hidden, int no_heads, int no_qk_poin
  *                operands in tensor memory; default)
  *   "gemm_impl": 0 = fp32 CUDA-core GEMM, 1 = 3xFP16 mma.sync GEMM, 2 = 3xFP16 tcgen05 GEMM for the K = 128
  *                layers that are given a workspace, mma.sync otherwise (default)
- *   "ipa_impl" : 0 = CUDA-core attention, 1 = tensor-core attention (16-key tiles, fragments from L2),
- *                2 = tensor-core attention with point distances folded into Q K^T and the K/V fragments of a
- *                    key tile bulk-copied into shared memory,
- *                3 = the same arithmetic, warp-specialised (head warps / pair warps, TMA z ring),
- *                4 = variant 3 with the pair warps decoupled (default): the pair bias of the next key tile is
- *                    computed before the o_pair accumulation of the current one (6-slot z row ring), Q' fragments
- *                    parked in tensor memory so the pair warps get 88 registers
+ *   "ipa_impl" : 0 = fp32 CUDA-core attention (cross-check), 3 = tensor-core attention (point-distance term folded into
+ *                the Q K^T contraction, K'/V' fragments of a key tile bulk-copied into shared memory, head warps / pair
+ *                warps, TMA z ring), 4 = variant 3 with the pair warps decoupled (default): the pair bias of the next key
+ *                tile is computed before the o_pair accumulation of the current one (6-slot z row ring), Q' fragments
+ *                parked in tensor memory so the pair warps get 88 registers
  *   "chain_impl": 1 = the K = 128 node layers between the attention kernels run as fused layer chains (one
  *                kernel per chain, activations in tensor memory; needs gemm_impl = 2 and prepacked weights;
  *                default), 0 = one GEMM / LayerNorm launch per layer
- *   "pack_impl" : IPA operand packing for ipa_impl 3 / 4: 1 = persistent double-buffered kernel (bulk copies of the
- *                next key tile under the conversion of the current one; default), 0 = one CTA per key tile
  *   "edge_terms": split-precision products the tcgen05 edge kernel issues per GEMM (error budget:
  *                profiles/r2_edge_error_budget.txt).  Bit g (0: z W1z^T, 1: z Wfz^T, 2: h1 W2^T, 3: h2 Wf^T) set =
  *                that GEMM drops its A_hi W_lo product (two passes instead of three).  Default 0: three passes everywhere.
+ *   "mma_order" : issue order of the three split products in the tcgen05 GEMM kernels: 1 = all small cross products of a
+ *                K chunk before its hi x hi products (the tensor-memory accumulator is truncated after every MMA; small
+ *                terms first keeps most of those roundings at the 2^-11 scale: scripts/gpu_gemm_error.py), 0 = interleaved
  */
 int pf_set_option(const char* name, int value);
 int pf_get_option(const char* name);

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libpepflow_b200.so")
-SOURCES = ["pf_api.cu", "pf_gemm.cu", "pf_gemm_umma.cu", "pf_node.cu", "pf_ipa.cu", "pf_ipa_tc.cu", "pf_ipa_v2.cu", "pf_edge.cu", "pf_edge_umma.cu", "pf_euler.cu", "pf_embed.cu", "pf_recon.cu"]
+SOURCES = ["pf_api.cu", "pf_gemm.cu", "pf_gemm_umma.cu", "pf_node.cu", "pf_ipa.cu", "pf_ipa_v2.cu", "pf_edge.cu", "pf_edge_umma.cu", "pf_euler.cu", "pf_embed.cu", "pf_recon.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-I", os.path.join(ROOT, "include"), "-I", CSRC] + os.environ.get("PF_NVCC_EXTRA", "").split()
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
                     print(out)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-Xlinker", "--no-undefined"])
     return LIB
 
 

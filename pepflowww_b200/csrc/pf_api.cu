@@ -12,7 +12,7 @@ namespace pf {
 
 static std::atomic<int64_t> g_launches{0};
 static int g_num_sms = 148;
-static std::atomic<int> g_edge_impl{2}, g_gemm_impl{2}, g_ipa_impl{4}, g_chain_impl{1}, g_pack_impl{1}, g_edge_terms{0};
+static std::atomic<int> g_edge_impl{2}, g_gemm_impl{2}, g_ipa_impl{4}, g_chain_impl{1}, g_edge_terms{0}, g_mma_order{1};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -52,8 +52,8 @@ int opt_edge_impl() { return g_edge_impl.load(std::memory_order_relaxed); }
 int opt_gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
 int opt_ipa_impl() { return g_ipa_impl.load(std::memory_order_relaxed); }
 int opt_chain_impl() { return g_chain_impl.load(std::memory_order_relaxed); }
-int opt_pack_impl() { return g_pack_impl.load(std::memory_order_relaxed); }
 int opt_edge_terms() { return g_edge_terms.load(std::memory_order_relaxed); }
+int opt_mma_order() { return g_mma_order.load(std::memory_order_relaxed); }
 void edge_umma_resolve_driver();
 
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -227,7 +227,6 @@ int pf_init(int device) {
   pf::g_num_sms = sms;
   pf::node_kernels_init();
   pf::ipa_kernels_init();
-  pf::ipa_tc_kernels_init();
   pf::ipa_v2_kernels_init();
   pf::edge_kernels_init();
   pf::gemm_umma_init();
@@ -249,10 +248,10 @@ int pf_set_option(const char* name, int value) {
   if (!name) return PF_ERR_NULL_POINTER;
   if (!std::strcmp(name, "edge_impl") && (value >= 0 && value <= 2)) { pf::g_edge_impl = value; return PF_OK; }
   if (!std::strcmp(name, "gemm_impl") && (value >= 0 && value <= 2)) { pf::g_gemm_impl = value; return PF_OK; }
-  if (!std::strcmp(name, "ipa_impl") && (value >= 0 && value <= 4)) { pf::g_ipa_impl = value; return PF_OK; }
+  if (!std::strcmp(name, "ipa_impl") && (value == 0 || value == 3 || value == 4)) { pf::g_ipa_impl = value; return PF_OK; }
   if (!std::strcmp(name, "chain_impl") && (value >= 0 && value <= 1)) { pf::g_chain_impl = value; return PF_OK; }
-  if (!std::strcmp(name, "pack_impl") && (value >= 0 && value <= 1)) { pf::g_pack_impl = value; return PF_OK; }
   if (!std::strcmp(name, "edge_terms") && (value >= 0 && value <= 15)) { pf::g_edge_terms = value; return PF_OK; }
+  if (!std::strcmp(name, "mma_order") && (value >= 0 && value <= 1)) { pf::g_mma_order = value; return PF_OK; }
   return PF_ERR_BAD_OPTION;
 }
 
@@ -262,8 +261,8 @@ int pf_get_option(const char* name) {
   if (!std::strcmp(name, "gemm_impl")) return pf::opt_gemm_impl();
   if (!std::strcmp(name, "ipa_impl")) return pf::opt_ipa_impl();
   if (!std::strcmp(name, "chain_impl")) return pf::opt_chain_impl();
-  if (!std::strcmp(name, "pack_impl")) return pf::opt_pack_impl();
   if (!std::strcmp(name, "edge_terms")) return pf::opt_edge_terms();
+  if (!std::strcmp(name, "mma_order")) return pf::opt_mma_order();
   return PF_ERR_BAD_OPTION;
 }
 

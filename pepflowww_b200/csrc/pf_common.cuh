@@ -33,8 +33,8 @@ int opt_edge_impl();
 int opt_gemm_impl();
 int opt_ipa_impl();
 int opt_chain_impl();
-int opt_pack_impl();
 int opt_edge_terms();
+int opt_mma_order();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -146,10 +146,7 @@ int launch_mod_2pi(const float* x, float* y, int n, cudaStream_t st);
 int launch_quat_to_rot(const float* quat, float* rot, int n, cudaStream_t st);
 size_t ipa_workspace_bytes(int B, int L);
 int launch_ipa_attention(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
-int launch_ipa_attention_v1(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
-void ipa_tc_kernels_init();
 size_t ipa_v2_workspace_bytes(int B, int L);
-int launch_ipa_attention_v2(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st,
                             bool decoupled);
 void ipa_v2_kernels_init();

@@ -69,7 +69,9 @@ __device__ void so3_exp_dev(const float* w, float* R) {
 }
 
 // out = base * Exp(t * Log(base^T mat))   (so3_utils.py:486-520)
-__device__ void so3_geodesic_dev(float t, const float* mat, const float* base, float* out) {
+// __noinline__: every caller (so3_geodesic_kernel, euler_step_kernel, sampler_update_kernel) runs the SAME instruction
+// sequence, so the one-call iteration and the three-call iteration agree bit for bit (no per-call-site FMA contraction)
+__device__ __noinline__ void so3_geodesic_dev(float t, const float* mat, const float* base, float* out) {
   float rel[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -87,7 +89,7 @@ __device__ void so3_geodesic_dev(float t, const float* mat, const float* base, f
       out[i * 3 + j] = base[i * 3] * E[j] + base[i * 3 + 1] * E[3 + j] + base[i * 3 + 2] * E[6 + j];
 }
 
-__device__ __forceinline__ float tor_geodesic_dev(float t, float a1, float a0) {
+__device__ __noinline__ float tor_geodesic_dev(float t, float a1, float a0) {
   const float d = a1 - a0;
   return mod_2pi(a0 + t * atan2f(sinf(d), cosf(d)));
 }
@@ -115,7 +117,7 @@ __device__ __forceinline__ float uniform_for(const float* uniforms, uint64_t see
 
 // categorical draw from softmax(x[0..19]) + 1e-8 by inverse CDF (stands in for multinomial,
 // pepflow/modules/common/layers.py:17-22); same left-to-right fp32 prefix sums as the oracle.
-__device__ int categorical20(const float* x, float u) {
+__device__ __noinline__ int categorical20(const float* x, float u) {
   float mx = x[0];
 #pragma unroll
   for (int k = 1; k < 20; ++k) mx = fmaxf(mx, x[k]);
@@ -220,7 +222,7 @@ __global__ void euler_step_kernel(EulerArgs a) {
 #pragma unroll
   for (int e = 0; e < 3; ++e) {
     const size_t o = (size_t)i * 3 + e;
-    const float v = a.trans_t[o] + (a.c_trans[o] - a.trans0[o]) * dt;
+    const float v = __fadd_rn(a.trans_t[o], __fmul_rn(a.c_trans[o] - a.trans0[o], dt));   // two roundings, like torch
     a.trans_o[o] = g ? v : a.trans1[o];
   }
   // rotations (:322-323): geodesic with the fixed 10 d_t schedule
@@ -239,7 +241,7 @@ __global__ void euler_step_kernel(EulerArgs a) {
   for (int k = 0; k < 20; ++k) {
     const size_t o = (size_t)i * 20 + k;
     const float target = (sh == k) ? a.k : -a.k;
-    sx[k] = a.simplex_t[o] + (target - a.simplex0[o]) * dt;
+    sx[k] = __fadd_rn(a.simplex_t[o], __fmul_rn(target - a.simplex0[o], dt));
     a.simplex_o[o] = sx[k];
   }
   int64_t s2 = a.seq1[i];
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(SU_T) sampler_update_kernel(SamplerArgs a) {
     su_load<3, 3>(stage, a.trans_t, r0, nr, xt);
     su_load<3, 3>(stage, a.trans0, r0, nr, x0);
 #pragma unroll
-    for (int e = 0; e < 3; ++e) xt[e] = (g && a.sample_bb) ? xt[e] + (c_trans[e] - x0[e]) * dt : trans1[e];
+    for (int e = 0; e < 3; ++e) xt[e] = (g && a.sample_bb) ? __fadd_rn(xt[e], __fmul_rn(c_trans[e] - x0[e], dt)) : trans1[e];
     su_store<3, 3>(stage, a.trans_t, r0, nr, xt);
   }
   // rotations (:322-323): geodesic with the fixed 10 d_t schedule
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(SU_T) sampler_update_kernel(SamplerArgs a) {
     su_load<20, SU_PITCH>(stage, a.simplex_t, r0, nr, sx);
     su_load<20, SU_PITCH>(stage, a.simplex0, r0, nr, s0);
 #pragma unroll
-    for (int k = 0; k < 20; ++k) sx[k] = sx[k] + (((c_seq == k) ? a.k : -a.k) - s0[k]) * dt;
+    for (int k = 0; k < 20; ++k) sx[k] = __fadd_rn(sx[k], __fmul_rn(((c_seq == k) ? a.k : -a.k) - s0[k], dt));
     su_store<20, SU_PITCH>(stage, a.simplex_t, r0, nr, sx);
     if (g) {
       const float* u = a.uniforms ? a.uniforms + (size_t)(2 * n + 1) * a.n : nullptr;

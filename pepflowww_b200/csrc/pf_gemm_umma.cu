@@ -59,6 +59,7 @@ struct alignas(64) GemmUArgs {
   const float* x; const float* bias; const float* rowmask;
   const uint4* wpack;
   int M, N, ntiles, act;
+  int small_first;           // "mma_order" option
 };
 
 __global__ void __launch_bounds__(GU_THREADS, 1) gemm_umma_kernel(const __grid_constant__ GemmUArgs a) {
@@ -179,17 +180,32 @@ __global__ void __launch_bounds__(GU_THREADS, 1) gemm_umma_kernel(const __grid_c
       tc_fence_after();
       const uint32_t wt = sbase + GU_SM_W + buf * GU_TILE_BYTES;
       const uint32_t d = tmem + GU_COL_ACC + 128 * buf;
+      // Small products first ("mma_order" = 1): the accumulator is rounded after every MMA, and the two cross products are
+      // 2^-11 of the main one - summing all of them before the first hi x hi product keeps their rounding errors at that
+      // scale instead of spending 24 roundings at full magnitude
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t dh = smem_desc(wt + ks * 4096, 2048, 128);
-        const uint64_t dl = smem_desc(wt + 32768 + ks * 4096, 2048, 128);
-        const uint32_t a_hi = tmem + GU_COL_A + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
-        if (elect_one()) {
-          mma_cta_ts(d, a_lo, dh, idesc, ks == 0 ? 0u : 1u);
-          mma_cta_ts(d, a_hi, dl, idesc, 1u);
-          mma_cta_ts(d, a_hi, dh, idesc, 1u);
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t dh = smem_desc(wt + ks * 4096, 2048, 128);
+          const uint64_t dl = smem_desc(wt + 32768 + ks * 4096, 2048, 128);
+          const uint32_t a_hi = tmem + GU_COL_A + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
+          if (elect_one()) {
+            if (a.small_first) {
+              if (pass == 0) {
+                mma_cta_ts(d, a_lo, dh, idesc, ks == 0 ? 0u : 1u);
+                mma_cta_ts(d, a_hi, dl, idesc, 1u);
+              } else {
+                mma_cta_ts(d, a_hi, dh, idesc, 1u);
+              }
+            } else if (pass == 0) {
+              mma_cta_ts(d, a_lo, dh, idesc, ks == 0 ? 0u : 1u);
+              mma_cta_ts(d, a_hi, dl, idesc, 1u);
+              mma_cta_ts(d, a_hi, dh, idesc, 1u);
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (elect_one()) {
         commit_cta(bar(GU_BAR_WEMPTY + buf));     // the W stage can be refilled once these MMAs have read it
@@ -262,6 +278,7 @@ struct alignas(64) ChainArgs {
   ChainStage st[CH_MAXS];
   const float* x;                // [M, 128 * kchunks] input of the first layer
   int M, nstages;
+  int small_first;               // "mma_order" option
   int kchunks;                   // > 1: the first layer contracts K = 128 * kchunks (its W image holds one tile per
                                  // 128-column chunk); the chunks alternate between two A buffers (the second one
                                  // borrows the residual columns) and accumulate into one tile
@@ -477,16 +494,28 @@ __global__ void __launch_bounds__(GU_THREADS, 1) node_chain_kernel(const __grid_
           tc_fence_after();
           const uint32_t wt = sbase + GU_SM_W + buf * GU_TILE_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t dh = smem_desc(wt + ks * 4096, 2048, 128);
-            const uint64_t dl = smem_desc(wt + 32768 + ks * 4096, 2048, 128);
-            const uint32_t a_hi = tmem + acol + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
-            if (elect_one()) {
-              mma_cta_ts(d, a_lo, dh, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
-              mma_cta_ts(d, a_hi, dl, idesc, 1u);
-              mma_cta_ts(d, a_hi, dh, idesc, 1u);
+          for (int pass = 0; pass < 2; ++pass) {            // "mma_order" = 1: the small cross products first (see above)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t dh = smem_desc(wt + ks * 4096, 2048, 128);
+              const uint64_t dl = smem_desc(wt + 32768 + ks * 4096, 2048, 128);
+              const uint32_t a_hi = tmem + acol + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
+              if (elect_one()) {
+                if (a.small_first) {
+                  if (pass == 0) {
+                    mma_cta_ts(d, a_lo, dh, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+                    mma_cta_ts(d, a_hi, dl, idesc, 1u);
+                  } else {
+                    mma_cta_ts(d, a_hi, dh, idesc, 1u);
+                  }
+                } else if (pass == 0) {
+                  mma_cta_ts(d, a_lo, dh, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+                  mma_cta_ts(d, a_hi, dl, idesc, 1u);
+                  mma_cta_ts(d, a_hi, dh, idesc, 1u);
+                }
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
           if (elect_one()) {
             commit_cta(bar(GU_BAR_WEMPTY + buf));
@@ -535,7 +564,7 @@ int launch_linear_umma(const float* x, const float* w, int ldw, const float* bia
   GemmUArgs a;
   PF_TRY(encode_y_map(&a.tm_y, y, M, N));
   a.x = x; a.bias = bias; a.rowmask = rowmask; a.wpack = static_cast<const uint4*>(wpack);
-  a.M = M; a.N = N; a.ntiles = ntiles; a.act = act;
+  a.M = M; a.N = N; a.ntiles = ntiles; a.act = act; a.small_first = opt_mma_order();
   gemm_umma_kernel<<<(M + 127) / 128, GU_THREADS, GU_SMEM, st>>>(a);
   PF_CHECK_LAUNCH();
   return PF_OK;
@@ -565,7 +594,7 @@ int launch_node_chain(const float* x, int M, const NodeChainStage* stages, int n
       PF_TRY(encode_y_map(&a.tm[s], h.out, M, h.N));
     }
   }
-  a.x = x; a.M = M; a.nstages = n; a.kchunks = kchunks;
+  a.x = x; a.M = M; a.nstages = n; a.kchunks = kchunks; a.small_first = opt_mma_order();
   node_chain_kernel<<<(M + 127) / 128, GU_THREADS, GU_SMEM, st>>>(a);
   PF_CHECK_LAUNCH();
   return PF_OK;

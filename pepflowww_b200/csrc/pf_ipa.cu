@@ -208,8 +208,6 @@ int launch_ipa_attention(const IpaArgs& a, void* workspace, size_t workspace_byt
   if (a.B == 0 || a.L == 0) return PF_OK;
   if (opt_ipa_impl() == 4) return launch_ipa_attention_v3(a, workspace, workspace_bytes, st, true);
   if (opt_ipa_impl() == 3) return launch_ipa_attention_v3(a, workspace, workspace_bytes, st, false);
-  if (opt_ipa_impl() == 2) return launch_ipa_attention_v2(a, workspace, workspace_bytes, st);
-  if (opt_ipa_impl() == 1) return launch_ipa_attention_v1(a, workspace, workspace_bytes, st);
   const size_t smem = ipa_v0_smem(a.L);
   if (smem > 227 * 1024) return PF_ERR_BAD_SHAPE;  // L <= ~1600
   dim3 grid((a.L + TI - 1) / TI, a.B);

@@ -1,19 +1,21 @@
-// K3, variant 2 ("ipa_impl" = 2): tensor-core fused invariant-point attention with every operand of a key
-// tile resident in shared memory before it is needed (models_con/ipa_pytorch.py:393-473).
+// K3: tensor-core fused invariant-point attention (models_con/ipa_pytorch.py:393-473), "ipa_impl" 3 / 4 (default 4).
 //
-// Differences to variant 1 (pf_ipa_tc.cu), all aimed at the exposed L2 latency that dominated it:
-//   * The point-distance term rides on the tensor core.  -1/2 c_h sum_p |q_p - k_p|^2 =
-//     c_h q.k - 1/2 c_h |k|^2 - 1/2 c_h |q|^2: the last term is constant along a softmax row and drops out,
-//     the first extends the scalar Q K^T contraction from 128 to 152 channels (Q' = [q/sqrt(3C) | c_h q_pts],
-//     K' = [k | k_pts]), the middle one is a per-(key, head) bias computed once by the pack kernel in fp32.
-//     (3xFP16 split products; the cancellation is bounded by 2^-22 |q||k| c_h ~ 3e-5 on a logit.)
+//   * The point-distance term rides on the tensor core, arranged so that nothing of the size |t|^2 is ever rounded.
+//     With q_p = t_i + a_ip, k_p = t_j + b_jp (a, b = the ROTATED local points; t = frame translations),
+//       sum_p |q_p - k_p|^2 = P |t_i - t_j|^2 + 2 (t_i - t_j).(A_i - B_j) + sum_p |a_ip - b_jp|^2,   A = sum_p a, B = sum_p b.
+//     Terms constant along a softmax row drop out; what is left of  -1/2 c_h sum_p |q_p - k_p|^2  is
+//       -P/2 c_h |t_i - t_j|^2                         exact fp32 per pair in the head warps (key translations ride in the blob)
+//       + c_h (t_i.B_j + A_i.t_j + sum_p a_ip.b_jp)      30 more channels of the scalar Q K^T contraction (128 -> 158 of 160):
+//                                                      Q' = [q/sqrt(3C) | c_h t_i | c_h A_i | c_h a_ip],  K' = [k | B_j | t_j | b_jp]
+//       - c_h t_j.B_j - 1/2 c_h sum_p |b_jp|^2          per-(key, head) bias computed once by the pack kernel in fp32.
+//     The products that reach the accumulator are of size |t| |B| c_h (~75 at 47 A) instead of P |t|^2 c_h (~1800): the
+//     expanded form  c_h q.k - 1/2 c_h |k|^2  of round 1 lost 1e-4 on a logit to fp32 cancellation at the bench shape.
 //   * Keys are streamed in tiles of 8.  The pre-packed K' and V' fragments of all heads for one tile, the key
-//     biases and the key mask form ONE contiguous 84 KB blob per (complex, key tile) that a single bulk copy
-//     (TMA engine, mbarrier completion) lands in shared memory while the previous tile is finished; the MMA
+//     biases, key mask and key translations form one contiguous blob per (complex, key tile); every head warp bulk-copies
+//     the slice of its head (TMA engine, mbarrier completion) while the previous tile is finished; the MMA
 //     operands are then conflict-free 16 / 8 byte shared-memory loads instead of L2 round trips.
-//   * z tiles [16 i x 8 j x 64] keep the 2-stage cp.async ring.
-// CTA = 16 query rows x 8 heads; warp roles alternate between pair-major (pair bias W_b z on the tensor core,
-// o_pair accumulation) and head-major (Q'K'^T, online softmax, P V with m16n8k8) as in variant 1.
+// CTA = 16 query rows x 8 heads; 8 head warps (Q'K'^T, online softmax, P V) and 8 pair warps (pair bias W_b z on the
+// tensor core, o_pair accumulation) - see the kernel below.
 #include <cuda.h>   // CUtensorMap
 
 #include "pf_common.cuh"
@@ -26,252 +28,50 @@ using namespace umma;
 
 constexpr int V2_TQ = 16, V2_TK = 8;
 constexpr int V2_ZP = 68;            // padded pair row (floats)
-constexpr int V2_KS = 10;            // K steps of Q'K'^T: 128 scalar + 24 point + 8 zero channels
+constexpr int V2_KS = 10;            // K steps of Q'K'^T: 128 scalar + 30 point-term + 2 zero channels
+constexpr int V2_KPW = 6 + PQ * 3;   // 30 point-term channels per head: [B | t | b_p] (keys), [t | A | a_p] (queries)
 constexpr int V2_VNT = 21;           // n-tiles of [v(128) | v_pts(36) | pad(4)]
 constexpr int V2_BLOB_K = H * V2_KS * 32 * 16;    // 40960: [h][ks][lane] uint4 {hi b0, hi b1, lo b0, lo b1}
 constexpr int V2_BLOB_V = H * V2_VNT * 32 * 8;    // 43008: [h][nt][lane] uint2 {hi, lo}
-constexpr int V2_BLOB_KB = H * V2_TK * 4;         // 256:   [h][key] fp32  -1/2 c_h |k_pts|^2
+constexpr int V2_BLOB_KB = H * V2_TK * 4;         // 256:   [h][key] fp32  -c_h t_j.B_j - 1/2 c_h sum |b_jp|^2
 constexpr int V2_BLOB_M = V2_TK * 4;              // 32:    [key] fp32 residue mask
-constexpr int V2_BLOB = V2_BLOB_K + V2_BLOB_V + V2_BLOB_KB + V2_BLOB_M;   // 84256 (multiple of 16)
-// blob layout: K' | key bias | key mask | V'   (the first three are needed first and form one bulk copy in v3)
-constexpr int V2_OFF_KB = V2_BLOB_K, V2_OFF_M = V2_OFF_KB + V2_BLOB_KB, V2_OFF_V = V2_OFF_M + V2_BLOB_M;
-constexpr int V2_BLOB_HEAD = V2_OFF_V;            // 41248 bytes: K' + key bias + mask
-static_assert(V2_OFF_V % 16 == 0, "V' part must stay 16-byte aligned");
+constexpr int V2_BLOB_T = V2_TK * 4 * 4;          // 128:   [key][4] fp32 frame translation (x, y, z, 0)
+constexpr int V2_BLOB = V2_BLOB_K + V2_BLOB_V + V2_BLOB_KB + V2_BLOB_M + V2_BLOB_T;   // 84384 (multiple of 16)
+// blob layout: K' | key bias | key mask | key translations | V'
+constexpr int V2_OFF_KB = V2_BLOB_K, V2_OFF_M = V2_OFF_KB + V2_BLOB_KB, V2_OFF_T = V2_OFF_M + V2_BLOB_M,
+              V2_OFF_V = V2_OFF_T + V2_BLOB_T;
+static_assert(V2_OFF_V % 16 == 0 && V2_BLOB % 16 == 0, "V' part / blobs must stay 16-byte aligned");
 constexpr int V2_QTILE_U4 = V2_KS * 32 * 2;       // per (b, h, it): [ks][lane]{hi, lo} uint4
 constexpr float V2_QSCALE = 0.05103103630798288f; // sqrt(1/(3*128))
 
-struct IpaPack2Args {
-  const float* proj; const float* pts; const float* head_w; const float* mask;
-  unsigned char* blobs; uint4* Qp;
-  int B, L, JT, IT;
-};
-
-__device__ __forceinline__ float v2_kprime(const IpaPack2Args& a, size_t row, int h, int kk) {
-  if (kk < C) return a.proj[row * NPROJ + OFF_KV + h * 2 * C + kk];
-  if (kk < C + PQ * 3) return a.pts[(row * H + h) * (NPT * 3) + PQ * 3 + (kk - C)];
-  return 0.f;
-}
-__device__ __forceinline__ float v2_qprime(const IpaPack2Args& a, size_t row, int h, int kk, float ch) {
-  if (kk < C) return a.proj[row * NPROJ + OFF_Q + h * C + kk] * V2_QSCALE;
-  if (kk < C + PQ * 3) return a.pts[(row * H + h) * (NPT * 3) + (kk - C)] * ch;
-  return 0.f;
-}
-__device__ __forceinline__ float v2_vprime(const IpaPack2Args& a, size_t row, int h, int n) {
-  if (n < C) return a.proj[row * NPROJ + OFF_KV + h * 2 * C + C + n];
-  if (n < C + PV * 3) return a.pts[(row * H + h) * (NPT * 3) + 2 * PQ * 3 + (n - C)];
-  return 0.f;
-}
-
-// One CTA per key-tile blob (blockIdx.x < B * JT: K' / V' fragments, key bias, key mask of 8 keys, all heads) or
-// per query tile (the remaining B * IT CTAs: Q' fragments of 16 rows, all heads).  All index arithmetic is 32-bit
-// with compile-time divisors; reads touch whole 32-byte sectors, writes are contiguous.
-__global__ void __launch_bounds__(256) ipa_pack2_kernel(IpaPack2Args a) {
-  const int L = a.L;
-  const int nblob = a.B * a.JT;
-  const int tid = threadIdx.x;
-  if ((int)blockIdx.x < nblob) {
-    const int b = blockIdx.x / a.JT, jt = blockIdx.x - b * a.JT;
-    const size_t row0 = (size_t)b * L;
-    unsigned char* blob = a.blobs + (size_t)blockIdx.x * V2_BLOB;
-    for (int idx = tid; idx < H * V2_KS * 32; idx += 256) {           // K' [h][ks][lane]
-      const int lane = idx & 31, r = idx >> 5, ks = r % V2_KS, h = r / V2_KS;
-      const int g = lane >> 2, t = lane & 3, j = jt * V2_TK + g;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (j < L) {
-        const int kk = ks * 16 + 2 * t;
-        v[0] = v2_kprime(a, row0 + j, h, kk); v[1] = v2_kprime(a, row0 + j, h, kk + 1);
-        v[2] = v2_kprime(a, row0 + j, h, kk + 8); v[3] = v2_kprime(a, row0 + j, h, kk + 9);
-      }
-      uint4 o;
-      split_pair(v[0], v[1], o.x, o.z);
-      split_pair(v[2], v[3], o.y, o.w);
-      reinterpret_cast<uint4*>(blob)[idx] = o;
-    }
-    for (int idx = tid; idx < H * V2_VNT * 32; idx += 256) {          // V' [h][nt][lane]
-      const int lane = idx & 31, r = idx >> 5, nt = r % V2_VNT, h = r / V2_VNT;
-      const int g = lane >> 2, t = lane & 3, n = nt * 8 + g, j = jt * V2_TK + 2 * t;
-      const float v0 = (j < L) ? v2_vprime(a, row0 + j, h, n) : 0.f;
-      const float v1 = (j + 1 < L) ? v2_vprime(a, row0 + j + 1, h, n) : 0.f;
-      uint2 o;
-      split_pair(v0, v1, o.x, o.y);
-      reinterpret_cast<uint2*>(blob + V2_OFF_V)[idx] = o;
-    }
-    if (tid < (H + 1) * V2_TK) {                                       // key bias [h][key], key mask [key]
-      const int key = tid % V2_TK, h = tid / V2_TK, j = jt * V2_TK + key;
-      float* dst = reinterpret_cast<float*>(blob + V2_OFF_KB);
-      if (h == H) {
-        dst[H * V2_TK + key] = (j < L) ? a.mask[row0 + j] : 0.f;
-      } else {
-        float s = 0.f;
-        if (j < L) {
-          const float* kp = a.pts + ((row0 + j) * H + h) * (NPT * 3) + PQ * 3;
-#pragma unroll
-          for (int e = 0; e < PQ * 3; ++e) s = fmaf(kp[e], kp[e], s);
-        }
-        dst[h * V2_TK + key] = -0.5f * a.head_w[h] * s;
-      }
-    }
-    return;
-  }
-  const int qi = blockIdx.x - nblob;                                   // Q' [b][h][it][ks][lane]{hi, lo}
-  const int b = qi / a.IT, it = qi - b * a.IT;
-  const size_t row0 = (size_t)b * L;
-  for (int idx = tid; idx < H * V2_KS * 32; idx += 256) {
-    const int lane = idx & 31, r = idx >> 5, ks = r % V2_KS, h = r / V2_KS;
-    const int g = lane >> 2, t = lane & 3;
-    const float ch = a.head_w[h];
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.f;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int i = it * V2_TQ + g + half * 8;
-      if (i < L) {
-        const int kk = ks * 16 + 2 * t;
-        v[half * 2 + 0] = v2_qprime(a, row0 + i, h, kk, ch); v[half * 2 + 1] = v2_qprime(a, row0 + i, h, kk + 1, ch);
-        v[4 + half * 2 + 0] = v2_qprime(a, row0 + i, h, kk + 8, ch); v[4 + half * 2 + 1] = v2_qprime(a, row0 + i, h, kk + 9, ch);
-      }
-    }
-    uint4 hi, lo;
-    split_pair(v[0], v[1], hi.x, lo.x);
-    split_pair(v[2], v[3], hi.y, lo.y);
-    split_pair(v[4], v[5], hi.z, lo.z);
-    split_pair(v[6], v[7], hi.w, lo.w);
-    uint4* q = a.Qp + ((((size_t)b * H + h) * a.IT + it) * V2_KS + ks) * 64 + lane * 2;
-    q[0] = hi;
-    q[1] = lo;
-  }
-}
-
-// ---- variant 3 / 4 packer: the same blobs and Q' tiles straight from the projection and the frames.
-// The rows a CTA needs are first staged in shared memory with coalesced 16-byte loads (k | v of all heads, the
-// local-frame points), the points go to the global frame there (Rigid.apply, rigid_utils.py:1124-1136 - no separate
-// ipa_points pass, no pts buffer), and the fragments are then cut from shared memory; every HBM access is a full line.
-constexpr int P3_THREADS = 512;                  // two CTAs per SM: 32 warps to hide the shared-memory latency
+// ---- operand packers: K' / V' blobs (ipa_pack4_kernel) and Q' tiles (ipa_packq_kernel) straight from the projection
+// and the frames.  The rows a CTA needs are first staged in shared memory with coalesced loads / bulk copies, the local
+// points are rotated there (and the value points moved to the global frame, Rigid.apply, rigid_utils.py:1124-1136 - no
+// separate ipa_points pass, no points buffer), and the fragments are then cut from shared memory; every HBM access is a
+// full line.
+constexpr int P3_THREADS = 512;
 constexpr int P3_KVP = 2048 + 8;                  // padded k|v row (floats): fragment loads spread over the banks
 constexpr int P3_NP = PQ + PV;                    // 20 key / value points per head
-constexpr int P3_OFF_KV = 0;                                      // [8 keys][P3_KVP]
-constexpr int P3_OFF_LOC = P3_OFF_KV + V2_TK * P3_KVP;            // [8 keys][480] local-frame kv points (proj order)
-constexpr int P3_OFF_KP = P3_OFF_LOC + V2_TK * 480;               // [8 keys][8 h][24]  global k points [p][xyz]
-constexpr int P3_OFF_VP = P3_OFF_KP + V2_TK * H * PQ * 3;         // [8 keys][8 h][36]  global v points
-constexpr int P3_OFF_FR = P3_OFF_VP + V2_TK * H * PV * 3;         // [16 rows][12] rotation | translation
-constexpr int P3_SMEM = (P3_OFF_FR + V2_TQ * 12) * 4;
-// Q' CTA view of the same buffer: [16 rows][192] local q points at P3_OFF_LOC, [16 rows][8 h][24] global at P3_OFF_KP
-static_assert(V2_TQ * 192 <= V2_TK * 480 && V2_TQ * H * PQ * 3 <= V2_TK * H * (PQ + PV) * 3, "Q' staging fits");
 
 struct IpaPack3Args {
   const float* proj; const float* rot; const float* trans; const float* head_w; const float* mask;
   unsigned char* blobs; uint4* Qp;
   int B, L, JT, IT;
-  int q_only;                   // 1: the grid holds only the Q' tiles (the blobs come from ipa_pack4_kernel)
 };
 
-__global__ void __launch_bounds__(P3_THREADS) ipa_pack3_kernel(IpaPack3Args a) {
+// Q' tile of 16 query rows [b][h][it][ks][lane]{hi, lo}; shared memory: [16][192] local q points | [16][8 h][30]
+// point-term channels (t | A | a_p) | [16][12] frames
+constexpr int PQ_SMEM = (V2_TQ * 192 + V2_TQ * H * V2_KPW + V2_TQ * 12) * 4;
+__global__ void __launch_bounds__(P3_THREADS) ipa_packq_kernel(IpaPack3Args a) {
   extern __shared__ __align__(16) float p3[];
   const int L = a.L, tid = threadIdx.x;
-  const int nblob = a.q_only ? 0 : a.B * a.JT;
-  float* s_fr = p3 + P3_OFF_FR;
-  if ((int)blockIdx.x < nblob) {
-    const int b = blockIdx.x / a.JT, jt = blockIdx.x - b * a.JT, j0 = jt * V2_TK;
-    const size_t row0 = (size_t)b * L;
-    const int nk = min(V2_TK, L - j0);
-    float* s_kv = p3 + P3_OFF_KV;
-    float* s_loc = p3 + P3_OFF_LOC;
-    float* s_kp = p3 + P3_OFF_KP;
-    float* s_vp = p3 + P3_OFF_VP;
-    for (int i = tid; i < V2_TK * 512; i += P3_THREADS) {                    // k | v of all heads: 2048 floats per key
-      const int k = i >> 9, q = i & 511;
-      const float4 v = k < nk ? __ldg(reinterpret_cast<const float4*>(a.proj + (row0 + j0 + k) * NPROJ + OFF_KV) + q)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(s_kv + k * P3_KVP + 4 * q) = v;
-    }
-    for (int i = tid; i < V2_TK * 120; i += P3_THREADS) {                    // local kv points: 480 floats per key
-      const int k = i / 120, q = i - k * 120;
-      const float4 v = k < nk ? __ldg(reinterpret_cast<const float4*>(a.proj + (row0 + j0 + k) * NPROJ + OFF_KVP) + q)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(s_loc + k * 480 + 4 * q) = v;
-    }
-    if (tid < V2_TK * 12) {
-      const int k = tid / 12, e = tid - k * 12;
-      s_fr[tid] = k < nk ? (e < 9 ? a.rot[(row0 + j0 + k) * 9 + e] : a.trans[(row0 + j0 + k) * 3 + e - 9]) : 0.f;
-    }
-    __syncthreads();
-    for (int i = tid; i < V2_TK * H * P3_NP; i += P3_THREADS) {              // local -> global frame
-      const int k = i / (H * P3_NP), r = i - k * (H * P3_NP), h = r / P3_NP, pnt = r - h * P3_NP;
-      const float* lp = s_loc + k * 480 + h * P3_NP + pnt;            // [xyz][h][20]
-      const float lx = lp[0], ly = lp[H * P3_NP], lz = lp[2 * H * P3_NP];
-      const float* R = s_fr + k * 12;
-      float* dst = pnt < PQ ? s_kp + (k * H + h) * (PQ * 3) + pnt * 3 : s_vp + (k * H + h) * (PV * 3) + (pnt - PQ) * 3;
-      const bool on = k < nk;                                          // keys past the end stay exactly zero
-      dst[0] = on ? R[0] * lx + R[1] * ly + R[2] * lz + R[9] : 0.f;
-      dst[1] = on ? R[3] * lx + R[4] * ly + R[5] * lz + R[10] : 0.f;
-      dst[2] = on ? R[6] * lx + R[7] * ly + R[8] * lz + R[11] : 0.f;
-    }
-    __syncthreads();
-    unsigned char* blob = a.blobs + (size_t)blockIdx.x * V2_BLOB;
-#pragma unroll 5
-    for (int idx = tid; idx < H * V2_KS * 32; idx += P3_THREADS) {           // K' [h][ks][lane]
-      const int lane = idx & 31, r = idx >> 5, ks = r % V2_KS, h = r / V2_KS;
-      const int g = lane >> 2, t = lane & 3, kk = ks * 16 + 2 * t;
-      float v[4];
-      if (ks < C / 16) {
-        const float* src = s_kv + g * P3_KVP + h * 2 * C + kk;
-        const float2 x0 = *reinterpret_cast<const float2*>(src), x1 = *reinterpret_cast<const float2*>(src + 8);
-        v[0] = x0.x; v[1] = x0.y; v[2] = x1.x; v[3] = x1.y;
-      } else {
-        const float* src = s_kp + (g * H + h) * (PQ * 3);
-        const int e = kk - C;                                          // 0 .. 30, valid below 24
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ee = e + (q & 1) + (q >> 1) * 8;
-          v[q] = ee < PQ * 3 ? src[ee] : 0.f;
-        }
-      }
-      uint4 o;
-      split_pair(v[0], v[1], o.x, o.z);
-      split_pair(v[2], v[3], o.y, o.w);
-      reinterpret_cast<uint4*>(blob)[idx] = o;
-    }
-#pragma unroll 3
-    for (int idx = tid; idx < H * V2_VNT * 32; idx += P3_THREADS) {          // V' [h][nt][lane]
-      const int lane = idx & 31, r = idx >> 5, nt = r % V2_VNT, h = r / V2_VNT;
-      const int g = lane >> 2, t = lane & 3, n = nt * 8 + g, k0 = 2 * t;
-      float v0, v1;
-      if (n < C) {
-        v0 = s_kv[k0 * P3_KVP + h * 2 * C + C + n]; v1 = s_kv[(k0 + 1) * P3_KVP + h * 2 * C + C + n];
-      } else if (n < C + PV * 3) {
-        v0 = s_vp[(k0 * H + h) * (PV * 3) + n - C]; v1 = s_vp[((k0 + 1) * H + h) * (PV * 3) + n - C];
-      } else {
-        v0 = v1 = 0.f;
-      }
-      uint2 o;
-      split_pair(v0, v1, o.x, o.y);
-      reinterpret_cast<uint2*>(blob + V2_OFF_V)[idx] = o;
-    }
-    if (tid < (H + 1) * V2_TK) {                                       // key bias [h][key], key mask [key]
-      const int key = tid % V2_TK, h = tid / V2_TK, j = j0 + key;
-      float* dst = reinterpret_cast<float*>(blob + V2_OFF_KB);
-      if (h == H) {
-        dst[H * V2_TK + key] = (j < L) ? a.mask[row0 + j] : 0.f;
-      } else {
-        const float* kp = s_kp + (key * H + h) * (PQ * 3);
-        float sq = 0.f;
-#pragma unroll
-        for (int e = 0; e < PQ * 3; ++e) sq = fmaf(kp[e], kp[e], sq);
-        dst[h * V2_TK + key] = -0.5f * a.head_w[h] * sq;
-      }
-    }
-    return;
-  }
-  // ---- Q' tile of 16 query rows [b][h][it][ks][lane]{hi, lo}
-  const int qi = blockIdx.x - nblob;
+  const int qi = blockIdx.x;
   const int b = qi / a.IT, it = qi - b * a.IT, i0 = it * V2_TQ;
   const size_t row0 = (size_t)b * L;
   const int nr = min(V2_TQ, L - i0);
-  // q_only launches get a compact 25 KB layout (several CTAs per SM): local points | global points | frames
-  float* s_loc = a.q_only ? p3 : p3 + P3_OFF_LOC;                      // [16][192] local q points [xyz][h][8]
-  float* s_qp = a.q_only ? p3 + V2_TQ * 192 : p3 + P3_OFF_KP;          // [16][8 h][24] global q points
-  if (a.q_only) s_fr = p3 + 2 * V2_TQ * 192;
+  float* s_loc = p3;                                                   // [16][192] local q points [xyz][h][8]
+  float* s_qp = p3 + V2_TQ * 192;                                      // [16][8 h][30]
+  float* s_fr = s_qp + V2_TQ * H * V2_KPW;
   for (int i = tid; i < V2_TQ * 48; i += P3_THREADS) {
     const int k = i / 48, q = i - k * 48;
     const float4 v = k < nr ? __ldg(reinterpret_cast<const float4*>(a.proj + (row0 + i0 + k) * NPROJ + OFF_QP) + q)
@@ -283,16 +83,26 @@ __global__ void __launch_bounds__(P3_THREADS) ipa_pack3_kernel(IpaPack3Args a) {
     s_fr[tid] = k < nr ? (e < 9 ? a.rot[(row0 + i0 + k) * 9 + e] : a.trans[(row0 + i0 + k) * 3 + e - 9]) : 0.f;
   }
   __syncthreads();
-  for (int i = tid; i < V2_TQ * H * PQ; i += P3_THREADS) {
+  for (int i = tid; i < V2_TQ * H * PQ; i += P3_THREADS) {             // a_ip = R_i l_ip (rotation only)
     const int k = i / (H * PQ), r = i - k * (H * PQ), h = r / PQ, pnt = r - h * PQ;
     const float* lp = s_loc + k * 192 + h * PQ + pnt;
     const float lx = lp[0], ly = lp[H * PQ], lz = lp[2 * H * PQ];
     const float* R = s_fr + k * 12;
-    float* dst = s_qp + (k * H + h) * (PQ * 3) + pnt * 3;
+    float* dst = s_qp + (k * H + h) * V2_KPW + 6 + pnt * 3;
     const bool on = k < nr;
-    dst[0] = on ? R[0] * lx + R[1] * ly + R[2] * lz + R[9] : 0.f;
-    dst[1] = on ? R[3] * lx + R[4] * ly + R[5] * lz + R[10] : 0.f;
-    dst[2] = on ? R[6] * lx + R[7] * ly + R[8] * lz + R[11] : 0.f;
+    dst[0] = on ? R[0] * lx + R[1] * ly + R[2] * lz : 0.f;
+    dst[1] = on ? R[3] * lx + R[4] * ly + R[5] * lz : 0.f;
+    dst[2] = on ? R[6] * lx + R[7] * ly + R[8] * lz : 0.f;
+  }
+  __syncthreads();
+  if (tid < V2_TQ * H * 3) {                                           // t_i and A_i = sum_p a_ip
+    const int k = tid / (H * 3), r = tid - k * (H * 3), h = r / 3, x = r - h * 3;
+    float* row = s_qp + (k * H + h) * V2_KPW;
+    float sum = 0.f;
+#pragma unroll
+    for (int pnt = 0; pnt < PQ; ++pnt) sum += row[6 + pnt * 3 + x];
+    row[x] = s_fr[k * 12 + 9 + x];
+    row[3 + x] = sum;
   }
   __syncthreads();
   for (int idx = tid; idx < H * V2_KS * 32; idx += P3_THREADS) {
@@ -312,12 +122,12 @@ __global__ void __launch_bounds__(P3_THREADS) ipa_pack3_kernel(IpaPack3Args a) {
         v[half * 2] = x0.x * V2_QSCALE; v[half * 2 + 1] = x0.y * V2_QSCALE;
         v[4 + half * 2] = x1.x * V2_QSCALE; v[4 + half * 2 + 1] = x1.y * V2_QSCALE;
       } else {
-        const float* src = s_qp + (k * H + h) * (PQ * 3);
+        const float* src = s_qp + (k * H + h) * V2_KPW;
         const int e = kk - C;
-        v[half * 2] = e < PQ * 3 ? src[e] * ch : 0.f;
-        v[half * 2 + 1] = e + 1 < PQ * 3 ? src[e + 1] * ch : 0.f;
-        v[4 + half * 2] = e + 8 < PQ * 3 ? src[e + 8] * ch : 0.f;
-        v[4 + half * 2 + 1] = e + 9 < PQ * 3 ? src[e + 9] * ch : 0.f;
+        v[half * 2] = e < V2_KPW ? src[e] * ch : 0.f;
+        v[half * 2 + 1] = e + 1 < V2_KPW ? src[e + 1] * ch : 0.f;
+        v[4 + half * 2] = e + 8 < V2_KPW ? src[e + 8] * ch : 0.f;
+        v[4 + half * 2 + 1] = e + 9 < V2_KPW ? src[e + 9] * ch : 0.f;
       }
     }
     uint4 hi, lo;
@@ -337,9 +147,9 @@ __global__ void __launch_bounds__(P3_THREADS) ipa_pack3_kernel(IpaPack3Args a) {
 constexpr int P4_THREADS = 768;                                    // one CTA per SM: 24 warps cut fragments
 constexpr int P4_STAGE = V2_TK * P3_KVP + V2_TK * 480;            // floats per stage: k|v rows, local kv points
 constexpr int P4_OFF_KP = 2 * P4_STAGE;
-constexpr int P4_OFF_VP = P4_OFF_KP + V2_TK * H * PQ * 3;
+constexpr int P4_OFF_VP = P4_OFF_KP + V2_TK * H * V2_KPW;        // s_kp rows: [B | t | b_p] (30 floats)
 constexpr int P4_OFF_FR = P4_OFF_VP + V2_TK * H * PV * 3;
-constexpr int P4_OFF_BAR = P4_OFF_FR + V2_TK * 12;
+constexpr int P4_OFF_BAR = ((P4_OFF_FR + V2_TK * 12 + 1) & ~1);     // 8-byte aligned mbarriers
 constexpr int P4_SMEM = (P4_OFF_BAR + 4) * 4;
 static_assert((P3_KVP * 4) % 16 == 0 && (P4_STAGE * 4) % 16 == 0 && (V2_TK * P3_KVP * 4) % 16 == 0, "bulk-copy alignment");
 static_assert(P4_SMEM <= 232448, "shared memory budget");
@@ -387,16 +197,28 @@ __global__ void __launch_bounds__(P4_THREADS, 1) ipa_pack4_kernel(IpaPack3Args a
     __syncthreads();
     const float* s_kv = p4 + stage * P4_STAGE;
     const float* s_loc = s_kv + V2_TK * P3_KVP;
-    for (int i = tid; i < V2_TK * H * P3_NP; i += P4_THREADS) {        // local -> global frame
+    for (int i = tid; i < V2_TK * H * P3_NP; i += P4_THREADS) {        // key points: rotate; value points: rotate + translate
       const int k = i / (H * P3_NP), r = i - k * (H * P3_NP), h = r / P3_NP, pnt = r - h * P3_NP;
       const bool on = k < nk;                                          // keys past the end stay exactly zero
       const float* lp = s_loc + k * 480 + h * P3_NP + pnt;            // [xyz][h][20]
       const float lx = on ? lp[0] : 0.f, ly = on ? lp[H * P3_NP] : 0.f, lz = on ? lp[2 * H * P3_NP] : 0.f;
       const float* R = s_fr + k * 12;
-      float* dst = pnt < PQ ? s_kp + (k * H + h) * (PQ * 3) + pnt * 3 : s_vp + (k * H + h) * (PV * 3) + (pnt - PQ) * 3;
-      dst[0] = on ? R[0] * lx + R[1] * ly + R[2] * lz + R[9] : 0.f;
-      dst[1] = on ? R[3] * lx + R[4] * ly + R[5] * lz + R[10] : 0.f;
-      dst[2] = on ? R[6] * lx + R[7] * ly + R[8] * lz + R[11] : 0.f;
+      const bool isk = pnt < PQ;
+      float* dst = isk ? s_kp + (k * H + h) * V2_KPW + 6 + pnt * 3 : s_vp + (k * H + h) * (PV * 3) + (pnt - PQ) * 3;
+      const float tx = isk ? 0.f : R[9], ty = isk ? 0.f : R[10], tz = isk ? 0.f : R[11];
+      dst[0] = on ? R[0] * lx + R[1] * ly + R[2] * lz + tx : 0.f;
+      dst[1] = on ? R[3] * lx + R[4] * ly + R[5] * lz + ty : 0.f;
+      dst[2] = on ? R[6] * lx + R[7] * ly + R[8] * lz + tz : 0.f;
+    }
+    __syncthreads();
+    if (tid < V2_TK * H * 3) {                                         // B_j = sum_p b_jp and t_j in front of the points
+      const int k = tid / (H * 3), r = tid - k * (H * 3), h = r / 3, x = r - h * 3;
+      float* row = s_kp + (k * H + h) * V2_KPW;
+      float sum = 0.f;
+#pragma unroll
+      for (int pnt = 0; pnt < PQ; ++pnt) sum += row[6 + pnt * 3 + x];
+      row[x] = sum;
+      row[3 + x] = s_fr[k * 12 + 9 + x];                               // 0 for keys past the end
     }
     __syncthreads();
     unsigned char* out = a.blobs + (size_t)blob * V2_BLOB;
@@ -411,12 +233,12 @@ __global__ void __launch_bounds__(P4_THREADS, 1) ipa_pack4_kernel(IpaPack3Args a
           const float2 x0 = *reinterpret_cast<const float2*>(src), x1 = *reinterpret_cast<const float2*>(src + 8);
           v[0] = x0.x; v[1] = x0.y; v[2] = x1.x; v[3] = x1.y;
         } else {
-          const float* src = s_kp + (g * H + h) * (PQ * 3);
+          const float* src = s_kp + (g * H + h) * V2_KPW;
           const int e = kk - C;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int ee = e + (q & 1) + (q >> 1) * 8;
-            v[q] = ee < PQ * 3 ? src[ee] : 0.f;
+            v[q] = ee < V2_KPW ? src[ee] : 0.f;
           }
         }
       }
@@ -446,12 +268,16 @@ __global__ void __launch_bounds__(P4_THREADS, 1) ipa_pack4_kernel(IpaPack3Args a
       if (h == H) {
         dst[H * V2_TK + key] = (j < L) ? a.mask[row0 + j] : 0.f;
       } else {
-        const float* kp = s_kp + (key * H + h) * (PQ * 3);
+        const float* kp = s_kp + (key * H + h) * V2_KPW;               // [B | t | b_p]
         float sq = 0.f;
 #pragma unroll
-        for (int e = 0; e < PQ * 3; ++e) sq = fmaf(kp[e], kp[e], sq);
-        dst[h * V2_TK + key] = -0.5f * a.head_w[h] * sq;
+        for (int e = 0; e < PQ * 3; ++e) sq = fmaf(kp[6 + e], kp[6 + e], sq);
+        const float tb = kp[0] * kp[3] + kp[1] * kp[4] + kp[2] * kp[5];
+        dst[h * V2_TK + key] = -a.head_w[h] * (tb + 0.5f * sq);        // -c_h t_j.B_j - 1/2 c_h sum_p |b_jp|^2
       }
+    } else if (tid >= 128 && tid < 128 + V2_TK * 4) {                  // key translations [key][x y z 0]
+      const int key = (tid - 128) >> 2, x = (tid - 128) & 3;
+      reinterpret_cast<float*>(out + V2_OFF_T)[key * 4 + x] = x < 3 ? s_fr[key * 12 + 9 + x] : 0.f;
     }
     __syncthreads();                                                   // s_kp / s_vp / s_fr / this stage are free again
   }
@@ -464,27 +290,7 @@ __device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1,
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(b0));
 }
-__device__ __forceinline__ void v2_cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
-}
-
-// ---- shared memory (bytes)
-constexpr int V2_SM_ZSTAGE = V2_TQ * V2_TK * V2_ZP * 4;      // 34816
-constexpr int V2_SM_Z = 0;
-constexpr int V2_SM_BLOB = V2_SM_Z + 2 * V2_SM_ZSTAGE;       // 69632
-constexpr int V2_SM_OP = V2_SM_BLOB + V2_BLOB;               // o_pair_raw [16 i][8 h][64] fp32
 constexpr int V2_BP = 10;                                    // pitch of the bias rows [h][i][10]
-constexpr int V2_SM_BIAS = V2_SM_OP + V2_TQ * H * CZ * 4;
-constexpr int V2_PP = 68;                                    // pitch of the P rows [i][key 8][h 8] (+4)
-constexpr int V2_SM_P = V2_SM_BIAS + H * V2_TQ * V2_BP * 4;
-constexpr int V2_SM_ALPHA = V2_SM_P + V2_TQ * V2_PP * 4;     // [h][i]
-constexpr int V2_SM_L = V2_SM_ALPHA + H * V2_TQ * 4;         // [h][i] final 1/row sums
-constexpr int V2_SM_BAR = V2_SM_L + H * V2_TQ * 4;
-constexpr int V2_SMEM = V2_SM_BAR + 16;
-static_assert(V2_SM_BLOB % 16 == 0 && V2_SM_OP % 16 == 0 && V2_SM_P % 16 == 0, "alignment");
-static_assert(V2_SMEM <= 232448, "shared memory budget");
 
 struct Ipa2Args {
   IpaArgs a;
@@ -492,301 +298,7 @@ struct Ipa2Args {
   int JT, IT;
 };
 
-__global__ void __launch_bounds__(256, 1) ipa_attention_v2_kernel(Ipa2Args p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  float* zs = reinterpret_cast<float*>(smem + V2_SM_Z);
-  const unsigned char* blob = smem + V2_SM_BLOB;
-  float* sop = reinterpret_cast<float*>(smem + V2_SM_OP);
-  float* sbias = reinterpret_cast<float*>(smem + V2_SM_BIAS);
-  float* sP = reinterpret_cast<float*>(smem + V2_SM_P);
-  float* salpha = reinterpret_cast<float*>(smem + V2_SM_ALPHA);
-  float* sl = reinterpret_cast<float*>(smem + V2_SM_L);
-  const uint32_t bar = smem_u32(smem + V2_SM_BAR);
-  const IpaArgs& a = p.a;
-  const int L = a.L;
-  const int b = blockIdx.y, it = blockIdx.x, i0 = it * V2_TQ;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const size_t rowb = (size_t)b * L;
-  const int h = warp;                                  // head-major role
-  const float sc_b = 0.5773502691896257f;              // sqrt(1/3)
-
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  for (int idx = tid; idx < V2_TQ * H * CZ; idx += 256) sop[idx] = 0.f;
-  // W_b as B fragments (pair-bias mma): rows n = head (8), k = channel; sqrt(1/3) folded in
-  uint32_t wbh[4][2], wbl[4][2];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    const float* w = a.w_b + g * CZ + ks * 16 + 2 * t;
-    split_pair(w[0] * sc_b, w[1] * sc_b, wbh[ks][0], wbl[ks][0]);
-    split_pair(w[8] * sc_b, w[9] * sc_b, wbh[ks][1], wbl[ks][1]);
-  }
-  // Q' fragments of head h (hi / lo)
-  uint4 qh[V2_KS], ql[V2_KS];
-  {
-    const uint4* qp = p.Qp + (((size_t)b * H + h) * p.IT + it) * V2_QTILE_U4;
-#pragma unroll
-    for (int ks = 0; ks < V2_KS; ++ks) {
-      qh[ks] = qp[(ks * 32 + lane) * 2];
-      ql[ks] = qp[(ks * 32 + lane) * 2 + 1];
-    }
-  }
-  const float bbias = sc_b * a.b_b[h];
-  const float mi_lo = (i0 + g < L) ? a.mask[rowb + i0 + g] : 0.f;
-  const float mi_hi = (i0 + g + 8 < L) ? a.mask[rowb + i0 + g + 8] : 0.f;
-
-  float O[V2_VNT][4];
-#pragma unroll
-  for (int n = 0; n < V2_VNT; ++n) { O[n][0] = O[n][1] = O[n][2] = O[n][3] = 0.f; }
-  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
-
-  auto issue_z = [&](int jt) {
-    const int j0 = jt * V2_TK;
-    float* zd = zs + (jt & 1) * (V2_SM_ZSTAGE / 4);
-    for (int c = tid; c < V2_TQ * V2_TK * 16; c += 256) {          // 16-byte chunks: pair (i,j) x 16 chunks
-      const int ch = c & 15, pr = c >> 4, j = pr & 7, i = pr >> 3;
-      const bool ok = (i0 + i < L) && (j0 + j < L);
-      const float* src = a.z + (((rowb + (ok ? i0 + i : 0)) * L + (ok ? j0 + j : 0)) * CZ) + ch * 4;
-      v2_cp_async16_zfill(zd + pr * V2_ZP + ch * 4, src, ok);
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
-  auto issue_blob = [&](int jt) {   // one thread; the whole tile's K' / V' / key bias / mask in one bulk copy
-    mbar_arrive_expect_tx(bar, V2_BLOB);
-    bulk_g2s(smem_u32(smem + V2_SM_BLOB), p.blobs + ((size_t)b * p.JT + jt) * V2_BLOB, V2_BLOB, bar);
-  };
-
-  __syncthreads();                                     // barrier initialised, sop zeroed
-  issue_z(0);
-  if (tid == 0) issue_blob(0);
-
-  const float* skb = reinterpret_cast<const float*>(blob + V2_OFF_KB);   // [h][8] then mask [8]
-  for (int jt = 0; jt < p.JT; ++jt) {
-    const int j0 = jt * V2_TK;
-    asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();                                   // z tile jt visible; everyone finished tile jt-1
-    if (jt + 1 < p.JT) issue_z(jt + 1);
-    const float* zt = zs + (jt & 1) * (V2_SM_ZSTAGE / 4);
-
-    // ================= phase 1 (pair-major): pair bias for rows 2w, 2w+1 x 8 keys, all heads
-    {
-      float acc[2][4];                                 // small terms | hi*hi: two independent chains
-      acc[0][0] = acc[0][1] = acc[0][2] = acc[0][3] = 0.f;
-      acc[1][0] = acc[1][1] = acc[1][2] = acc[1][3] = 0.f;
-      const float* zr_lo = zt + ((2 * warp) * V2_TK + g) * V2_ZP;       // pair (row 2w,   key g)
-      const float* zr_hi = zt + ((2 * warp + 1) * V2_TK + g) * V2_ZP;   // pair (row 2w+1, key g)
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const int c = ks * 16 + 2 * t;
-        const float2 x0 = *reinterpret_cast<const float2*>(zr_lo + c);
-        const float2 x1 = *reinterpret_cast<const float2*>(zr_hi + c);
-        const float2 x2 = *reinterpret_cast<const float2*>(zr_lo + c + 8);
-        const float2 x3 = *reinterpret_cast<const float2*>(zr_hi + c + 8);
-        uint32_t ah[4], al[4];
-        split_pair(x0.x, x0.y, ah[0], al[0]);
-        split_pair(x1.x, x1.y, ah[1], al[1]);
-        split_pair(x2.x, x2.y, ah[2], al[2]);
-        split_pair(x3.x, x3.y, ah[3], al[3]);
-        mma16816(acc[0], al, wbh[ks][0], wbh[ks][1]);
-        mma16816(acc[1], ah, wbh[ks][0], wbh[ks][1]);
-        mma16816(acc[0], ah, wbl[ks][0], wbl[ks][1]);
-      }
-      // C: (pair g -> row 2w, key g; heads 2t, 2t+1), (pair g+8 -> row 2w+1, key g)
-      sbias[((2 * t) * V2_TQ + 2 * warp) * V2_BP + g] = acc[0][0] + acc[1][0];
-      sbias[((2 * t + 1) * V2_TQ + 2 * warp) * V2_BP + g] = acc[0][1] + acc[1][1];
-      sbias[((2 * t) * V2_TQ + 2 * warp + 1) * V2_BP + g] = acc[0][2] + acc[1][2];
-      sbias[((2 * t + 1) * V2_TQ + 2 * warp + 1) * V2_BP + g] = acc[0][3] + acc[1][3];
-    }
-    __syncthreads();                                   // (A) bias tile complete
-    mbar_wait(bar, jt & 1);                            // K' / V' / key bias / mask of this tile have landed
-
-    // ================= phase 2 (head-major): S = Q' K'^T for head h, 16 rows x 8 keys
-    float S[4];
-    {
-      float Sa[4] = {0.f, 0.f, 0.f, 0.f}, Sb[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint4* kp = reinterpret_cast<const uint4*>(blob) + (h * V2_KS) * 32 + lane;
-#pragma unroll
-      for (int ks = 0; ks < V2_KS; ++ks) {
-        const uint4 k0 = kp[ks * 32];
-        const uint32_t ah[4] = {qh[ks].x, qh[ks].y, qh[ks].z, qh[ks].w};
-        const uint32_t al[4] = {ql[ks].x, ql[ks].y, ql[ks].z, ql[ks].w};
-        mma16816(Sa, al, k0.x, k0.y);
-        mma16816(Sb, ah, k0.x, k0.y);
-        mma16816(Sa, ah, k0.z, k0.w);
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) S[e] = Sa[e] + Sb[e];
-    }
-    // ================= phase 3: logits, online softmax (row g: S[0..1], row g+8: S[2..3]; keys 2t, 2t+1)
-    {
-      float mx_lo = -INFINITY, mx_hi = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = 2 * t + e;
-        const bool valid = (j0 + j < L);
-        const float mj = skb[H * V2_TK + j];
-        const float kb = skb[h * V2_TK + j] + bbias;
-        const float b_lo = sbias[(h * V2_TQ + g) * V2_BP + j], b_hi = sbias[(h * V2_TQ + g + 8) * V2_BP + j];
-        float x_lo = S[e] + b_lo + kb + 1e5f * (mi_lo * mj - 1.f);
-        float x_hi = S[2 + e] + b_hi + kb + 1e5f * (mi_hi * mj - 1.f);
-        x_lo = valid ? x_lo : -INFINITY;
-        x_hi = valid ? x_hi : -INFINITY;
-        S[e] = x_lo; S[2 + e] = x_hi;
-        mx_lo = fmaxf(mx_lo, x_lo); mx_hi = fmaxf(mx_hi, x_hi);
-      }
-      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
-      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
-      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-      const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
-      const float al_lo = expf(m_lo - mn_lo), al_hi = expf(m_hi - mn_hi);   // exp(-inf) = 0 on the first tile
-      m_lo = mn_lo; m_hi = mn_hi;
-      float ps_lo = 0.f, ps_hi = 0.f;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float p_lo = expf(S[e] - mn_lo), p_hi = expf(S[2 + e] - mn_hi);
-        S[e] = p_lo; S[2 + e] = p_hi;
-        ps_lo += p_lo; ps_hi += p_hi;
-        const int j = 2 * t + e;
-        sP[g * V2_PP + j * 8 + h] = p_lo;
-        sP[(g + 8) * V2_PP + j * 8 + h] = p_hi;
-      }
-      l_lo = l_lo * al_lo + ps_lo;
-      l_hi = l_hi * al_hi + ps_hi;
-      if (t == 0) { salpha[h * V2_TQ + g] = al_lo; salpha[h * V2_TQ + g + 8] = al_hi; }
-#pragma unroll
-      for (int n = 0; n < V2_VNT; ++n) { O[n][0] *= al_lo; O[n][1] *= al_lo; O[n][2] *= al_hi; O[n][3] *= al_hi; }
-    }
-    // ================= phase 4: O += P [V | v_pts]   (m16n8k8: K = the 8 keys of the tile)
-    {
-      uint32_t ph0, pl0, ph1, pl1;
-      split_pair(S[0], S[1], ph0, pl0);                // a0: row g,   keys 2t, 2t+1
-      split_pair(S[2], S[3], ph1, pl1);                // a1: row g+8
-      const uint2* vp = reinterpret_cast<const uint2*>(blob + V2_OFF_V) + (h * V2_VNT) * 32 + lane;
-#pragma unroll
-      for (int n = 0; n < V2_VNT; ++n) {
-        const uint2 v = vp[n * 32];
-        mma1688(O[n], pl0, pl1, v.x);
-        mma1688(O[n], ph0, ph1, v.y);
-        mma1688(O[n], ph0, ph1, v.x);
-      }
-    }
-    __syncthreads();                                   // (B) P tile and alpha complete; the blob has been consumed
-    if (tid == 0 && jt + 1 < p.JT) issue_blob(jt + 1);
-
-    // ================= phase 5 (pair-major): o_pair_raw[i, h, :] = alpha * old + sum_j P z
-#pragma unroll 1
-    for (int mt = 0; mt < 2; ++mt) {
-      const int i = 2 * warp + mt;
-      float acc[H][2];
-#pragma unroll
-      for (int hh = 0; hh < H; ++hh) {
-        const float al = salpha[hh * V2_TQ + i];
-        const float2 o = *reinterpret_cast<const float2*>(sop + (i * H + hh) * CZ + 2 * lane);
-        acc[hh][0] = o.x * al; acc[hh][1] = o.y * al;
-      }
-#pragma unroll
-      for (int j = 0; j < V2_TK; ++j) {
-        const float2 zv = *reinterpret_cast<const float2*>(zt + (i * V2_TK + j) * V2_ZP + 2 * lane);
-        const float4 p0 = *reinterpret_cast<const float4*>(sP + i * V2_PP + j * 8);
-        const float4 p1 = *reinterpret_cast<const float4*>(sP + i * V2_PP + j * 8 + 4);
-        const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-        for (int hh = 0; hh < H; ++hh) {
-          acc[hh][0] = fmaf(pv[hh], zv.x, acc[hh][0]);
-          acc[hh][1] = fmaf(pv[hh], zv.y, acc[hh][1]);
-        }
-      }
-#pragma unroll
-      for (int hh = 0; hh < H; ++hh)
-        *reinterpret_cast<float2*>(sop + (i * H + hh) * CZ + 2 * lane) = make_float2(acc[hh][0], acc[hh][1]);
-    }
-  }
-
-  // ================= epilogue
-  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
-  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-  const float il_lo = 1.0f / l_lo, il_hi = 1.0f / l_hi;
-  if (t == 0) { sl[h * V2_TQ + g] = il_lo; sl[h * V2_TQ + g + 8] = il_hi; }
-  __syncthreads();                                     // last tile's phase 5 done everywhere; zs is free
-  float* spt = zs;                                      // [8 h][16 i][40] normalised global-frame o_pt
-  {
-    const int i_lo = i0 + g, i_hi = i0 + g + 8;
-#pragma unroll
-    for (int n = 0; n < 16; ++n) {                      // o: channels 8n + 2t, +1
-      if (i_lo < L)
-        *reinterpret_cast<float2*>(a.feats + (rowb + i_lo) * NFEAT + h * C + n * 8 + 2 * t) =
-            make_float2(O[n][0] * il_lo, O[n][1] * il_lo);
-      if (i_hi < L)
-        *reinterpret_cast<float2*>(a.feats + (rowb + i_hi) * NFEAT + h * C + n * 8 + 2 * t) =
-            make_float2(O[n][2] * il_hi, O[n][3] * il_hi);
-    }
-#pragma unroll
-    for (int n = 16; n < V2_VNT; ++n) {
-      const int c = (n - 16) * 8 + 2 * t;
-      spt[(h * V2_TQ + g) * 40 + c] = O[n][0] * il_lo;
-      spt[(h * V2_TQ + g) * 40 + c + 1] = O[n][1] * il_lo;
-      spt[(h * V2_TQ + g + 8) * 40 + c] = O[n][2] * il_hi;
-      spt[(h * V2_TQ + g + 8) * 40 + c + 1] = O[n][3] * il_hi;
-    }
-  }
-  __syncthreads();
-  // o_pt: global -> local frame, norms (ipa_pytorch.py:455-460)
-  for (int idx = tid; idx < H * V2_TQ * PV; idx += 256) {
-    const int pnt = idx % PV, i = (idx / PV) % V2_TQ, hh = idx / (PV * V2_TQ);
-    if (i0 + i >= L) continue;
-    const float* R = a.rot + (rowb + i0 + i) * 9;
-    const float* tr = a.trans + (rowb + i0 + i) * 3;
-    const float* s = spt + (hh * V2_TQ + i) * 40 + pnt * 3;
-    const float gx = s[0] - tr[0], gy = s[1] - tr[1], gz = s[2] - tr[2];
-    const float lx = R[0] * gx + R[3] * gy + R[6] * gz;
-    const float ly = R[1] * gx + R[4] * gy + R[7] * gz;
-    const float lz = R[2] * gx + R[5] * gy + R[8] * gz;
-    float* f = a.feats + (rowb + i0 + i) * NFEAT + 1024;
-    f[0 * 96 + hh * PV + pnt] = lx;
-    f[1 * 96 + hh * PV + pnt] = ly;
-    f[2 * 96 + hh * PV + pnt] = lz;
-    f[3 * 96 + hh * PV + pnt] = sqrtf(lx * lx + ly * ly + lz * lz + 1e-8f);
-  }
-  // o_pair: down_z on the normalised a-weighted pair row (ipa_pytorch.py:469-473); W_dz staged in shared memory
-  __syncthreads();
-  float* swz = zs;                                      // [16 d][68]
-  for (int idx = tid; idx < 16 * CZ; idx += 256) swz[(idx >> 6) * V2_ZP + (idx & 63)] = a.w_dz[idx];
-  __syncthreads();
-  {
-    const int pairidx = tid >> 1, d0 = (tid & 1) * 8;   // pairidx = i * 8 + head
-    const int i = pairidx >> 3, hh = pairidx & 7;
-    if (i0 + i < L) {
-      const float* src = sop + (i * H + hh) * CZ;
-      float acc[8];
-#pragma unroll
-      for (int d = 0; d < 8; ++d) acc[d] = 0.f;
-#pragma unroll 4
-      for (int c = 0; c < CZ; c += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(src + c);
-#pragma unroll
-        for (int d = 0; d < 8; ++d) {
-          const float4 w = *reinterpret_cast<const float4*>(swz + (d0 + d) * V2_ZP + c);
-          acc[d] = fmaf(w.x, x.x, acc[d]);
-          acc[d] = fmaf(w.y, x.y, acc[d]);
-          acc[d] = fmaf(w.z, x.z, acc[d]);
-          acc[d] = fmaf(w.w, x.w, acc[d]);
-        }
-      }
-      const float inv = sl[hh * V2_TQ + i];
-      float* out = a.feats + (rowb + i0 + i) * NFEAT + 1024 + 384 + hh * 16 + d0;
-      float4 o0, o1;
-      o0.x = acc[0] * inv + a.b_dz[d0 + 0]; o0.y = acc[1] * inv + a.b_dz[d0 + 1];
-      o0.z = acc[2] * inv + a.b_dz[d0 + 2]; o0.w = acc[3] * inv + a.b_dz[d0 + 3];
-      o1.x = acc[4] * inv + a.b_dz[d0 + 4]; o1.y = acc[5] * inv + a.b_dz[d0 + 5];
-      o1.z = acc[6] * inv + a.b_dz[d0 + 6]; o1.w = acc[7] * inv + a.b_dz[d0 + 7];
-      *reinterpret_cast<float4*>(out) = o0;
-      *reinterpret_cast<float4*>(out + 4) = o1;
-    }
-  }
-}
+size_t ipa_workspace_bytes(int B, int L) { return ipa_v2_workspace_bytes(B, L); }
 
 size_t ipa_v2_workspace_bytes(int B, int L) {
   const size_t JT = (L + V2_TK - 1) / V2_TK, IT = (L + V2_TQ - 1) / V2_TQ;
@@ -815,7 +327,7 @@ constexpr int V4_SLOTS = 6;
 #endif
 // Every head warp owns the K' / V' slice of its head: it waits on its own mbarrier and refills the slice itself as
 // soon as IT is done with it - no CTA-wide free / full hand-off, the eight warps drift freely.
-constexpr int V3_KH = V2_KS * 32 * 16 + V2_TK * 4 + V2_TK * 4;   // 5184: K' fragments | key bias [8] | key mask [8]
+constexpr int V3_KH = V2_KS * 32 * 16 + V2_TK * 4 + V2_TK * 4 + V2_BLOB_T;   // 5312: K' fragments | key bias [8] | key mask [8] | key translations [8][4]
 constexpr int V3_VH = V2_VNT * 32 * 8;                            // 5376: V' fragments
 constexpr int V3_PH = 68;            // uint2 per head in a P tile (64 used; pitch = 8 words mod 32)
 template <bool DEC>
@@ -956,6 +468,15 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
     const float bbias = sc_b * a.b_b[h];
     const float mi_lo = (i0 + g < L) ? a.mask[rowb + i0 + g] : 0.f;
     const float mi_hi = (i0 + g + 8 < L) ? a.mask[rowb + i0 + g + 8] : 0.f;
+    // frame translations of this lane's two query rows and -P/2 c_h: the |t_i - t_j|^2 part of the point term is
+    // evaluated here in plain fp32, per pair
+    float ti_lo[3], ti_hi[3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      ti_lo[x] = (i0 + g < L) ? a.trans[(rowb + i0 + g) * 3 + x] : 0.f;
+      ti_hi[x] = (i0 + g + 8 < L) ? a.trans[(rowb + i0 + g + 8) * 3 + x] : 0.f;
+    }
+    const float c_dist = -0.5f * PQ * a.head_w[h];
     const unsigned char* kmine = smem + LT::SM_BLOB + h * V3_KH;
     const unsigned char* vmine = smem + LT::SM_VB + h * V3_VH;
     const float* skb = reinterpret_cast<const float*>(kmine + V2_KS * 32 * 16);   // key bias [8] then key mask [8]
@@ -966,7 +487,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
       mbar_arrive_expect_tx(my_kfull, V3_KH);
       bulk_g2s(dst, src + h * (V2_KS * 32 * 16), V2_KS * 32 * 16, my_kfull);
       bulk_g2s(dst + V2_KS * 32 * 16, src + V2_OFF_KB + h * (V2_TK * 4), V2_TK * 4, my_kfull);
-      bulk_g2s(dst + V2_KS * 32 * 16 + V2_TK * 4, src + V2_OFF_M, V2_TK * 4, my_kfull);
+      bulk_g2s(dst + V2_KS * 32 * 16 + V2_TK * 4, src + V2_OFF_M, V2_TK * 4 + V2_BLOB_T, my_kfull);   // mask | translations
     };
     auto issue_v = [&](int jt) {
       mbar_arrive_expect_tx(my_vfull, V3_VH);
@@ -982,7 +503,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
       // ---- S = Q' K'^T (16 rows x 8 keys)
       mbar_wait_cta(my_kfull, par);
       float S[4];
-      float kbv[2], mjv[2];
+      float kbv[4], mjv[2];                            // kbv: key bias + bias of linear_b + distance term, rows g | g+8
       {
         float Sc[4][4];                                // four independent accumulation chains (7-8 MMAs each)
 #pragma unroll
@@ -1020,7 +541,15 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
 #pragma unroll
         for (int e = 0; e < 4; ++e) S[e] = (Sc[0][e] + Sc[1][e]) + (Sc[2][e] + Sc[3][e]);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) { kbv[e] = skb[2 * t + e] + bbias; mjv[e] = skb[V2_TK + 2 * t + e]; }
+        for (int e = 0; e < 2; ++e) {
+          const float4 tj = *reinterpret_cast<const float4*>(skb + 2 * V2_TK + 4 * (2 * t + e));
+          const float ax = ti_lo[0] - tj.x, ay = ti_lo[1] - tj.y, az = ti_lo[2] - tj.z;
+          const float bx = ti_hi[0] - tj.x, by = ti_hi[1] - tj.y, bz = ti_hi[2] - tj.z;
+          const float kb = skb[2 * t + e] + bbias;
+          kbv[e] = kb + c_dist * (ax * ax + ay * ay + az * az);
+          kbv[2 + e] = kb + c_dist * (bx * bx + by * by + bz * bz);
+          mjv[e] = skb[V2_TK + 2 * t + e];
+        }
       }
       __syncwarp();                                    // this warp is done with its K' / key bias / mask of the tile
       if (lane == 0 && jt + 1 < JT) issue_k(jt + 1);
@@ -1036,7 +565,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) ipa_attention_v3_kernel(const _
           const bool valid = (j0 + j < L);
           const float b_lo = bs[(h * V2_TQ + g) * V2_BP + j], b_hi = bs[(h * V2_TQ + g + 8) * V2_BP + j];
           float x_lo = S[e] + b_lo + kbv[e] + 1e5f * (mi_lo * mjv[e] - 1.f);
-          float x_hi = S[2 + e] + b_hi + kbv[e] + 1e5f * (mi_hi * mjv[e] - 1.f);
+          float x_hi = S[2 + e] + b_hi + kbv[2 + e] + 1e5f * (mi_hi * mjv[e] - 1.f);
           x_lo = valid ? x_lo : -INFINITY;
           x_hi = valid ? x_hi : -INFINITY;
           S[e] = x_lo; S[2 + e] = x_hi;
@@ -1375,16 +904,13 @@ int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_
   const int JT = (a.L + V2_TK - 1) / V2_TK, IT = (a.L + V2_TQ - 1) / V2_TQ;
   unsigned char* blobs = static_cast<unsigned char*>(workspace);
   uint4* Qp = reinterpret_cast<uint4*>(blobs + (size_t)a.B * JT * V2_BLOB);
-  IpaPack3Args pa{a.proj, a.rot, a.trans, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT, 0};
+  IpaPack3Args pa{a.proj, a.rot, a.trans, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT};
   profile_begin(2, st);
-  if (opt_pack_impl() == 1) {
+  {
     const int nblob = a.B * JT;
     ipa_pack4_kernel<<<nblob < num_sms() ? nblob : num_sms(), P4_THREADS, P4_SMEM, st>>>(pa);
     PF_CHECK_LAUNCH();
-    pa.q_only = 1;
-    ipa_pack3_kernel<<<(unsigned)(a.B * IT), P3_THREADS, (2 * V2_TQ * 192 + V2_TQ * 12) * 4, st>>>(pa);
-  } else {
-    ipa_pack3_kernel<<<(unsigned)(a.B * JT + a.B * IT), P3_THREADS, P3_SMEM, st>>>(pa);
+    ipa_packq_kernel<<<(unsigned)(a.B * IT), P3_THREADS, PQ_SMEM, st>>>(pa);
   }
   profile_end(2, st);
   PF_CHECK_LAUNCH();
@@ -1399,27 +925,9 @@ int launch_ipa_attention_v3(const IpaArgs& a, void* workspace, size_t workspace_
   return PF_OK;
 }
 
-int launch_ipa_attention_v2(const IpaArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (a.B == 0 || a.L == 0) return PF_OK;
-  PF_REQUIRE(workspace && workspace_bytes >= ipa_v2_workspace_bytes(a.B, a.L), PF_ERR_WORKSPACE_TOO_SMALL);
-  const int JT = (a.L + V2_TK - 1) / V2_TK, IT = (a.L + V2_TQ - 1) / V2_TQ;
-  unsigned char* blobs = static_cast<unsigned char*>(workspace);
-  uint4* Qp = reinterpret_cast<uint4*>(blobs + (size_t)a.B * JT * V2_BLOB);
-  IpaPack2Args pa{a.proj, a.pts, a.head_w, a.mask, blobs, Qp, a.B, a.L, JT, IT};
-  ipa_pack2_kernel<<<(unsigned)(a.B * JT + a.B * IT), 256, 0, st>>>(pa);
-  PF_CHECK_LAUNCH();
-  Ipa2Args p{a, blobs, Qp, JT, IT};
-  profile_begin(0, st);
-  ipa_attention_v2_kernel<<<dim3(IT, a.B), 256, V2_SMEM, st>>>(p);
-  profile_end(0, st);
-  PF_CHECK_LAUNCH();
-  return PF_OK;
-}
-
 void ipa_v2_kernels_init() {
-  cudaFuncSetAttribute(ipa_pack3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM);
+  cudaFuncSetAttribute(ipa_packq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PQ_SMEM);
   cudaFuncSetAttribute(ipa_pack4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P4_SMEM);
-  cudaFuncSetAttribute(ipa_attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM);
   cudaFuncSetAttribute(ipa_attention_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3L<false>::SMEM);
   cudaFuncSetAttribute(ipa_attention_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3L<true>::SMEM);
 }

@@ -34,9 +34,9 @@ def model(dev, state_dict):
 
 
 @pytest.fixture(params=[(0, 0, 0, 1), (2, 2, 4, 1), (2, 2, 4, 0), (1, 0, 0, 1), (2, 0, 0, 1), (0, 1, 0, 1), (0, 2, 0, 1),
-                        (0, 2, 0, 0), (0, 0, 1, 1), (0, 0, 2, 1), (0, 0, 3, 1), (0, 0, 4, 1)],
+                        (0, 2, 0, 0), (0, 0, 3, 1), (0, 0, 4, 1)],
                 ids=["fp32", "tc", "tc_unfused_layers", "edge_mma_sync", "edge_tcgen05", "gemm_mma_sync", "gemm_tcgen05_chains",
-                     "gemm_tcgen05", "ipa_tc_v1", "ipa_tc_v2", "ipa_tc_v3", "ipa_tc_v4"])
+                     "gemm_tcgen05", "ipa_tc_v3", "ipa_tc_v4"])
 def impl(request):
     from pepflowww_b200 import _lib
     edge, gemm, ipa, chain = request.param
@@ -172,28 +172,27 @@ def test_ipa_module_golden(dev, model, tag, impl):
 
 
 @pytest.mark.parametrize("shape", [(2, 30), (3, 37), (2, 271)])
-def test_ipa_pack_variants_identical(dev, model, shape):
-    """The persistent double-buffered operand packer (pack_impl = 1) and the one-CTA-per-key-tile packer write the
-    same fragments: the IPA module output is bit-identical (ragged last key / query tiles included)."""
-    from pepflowww_b200 import _lib
+def test_ipa_module_vs_oracle_far_from_origin(dev, model, state_dict, shape):
+    """The point-distance term is evaluated as exact |t_i - t_j|^2 plus small-magnitude tensor-core products
+    (pf_ipa_v2.cu header): a complex translated 100 A away from the origin must give the same attention output as the
+    oracle, which forms the differences directly (ipa_pytorch.py:407-421) - ragged key / query tiles and a residue mask
+    included."""
     from pepflowww_b200.rigid import create_rigid
     B, L = shape
     gen = torch.Generator().manual_seed(L)
-    s = torch.randn(B, L, 128, generator=gen).to(dev)
-    z = torch.randn(B, L, L, 64, generator=gen).to(dev)
+    s = torch.randn(B, L, 128, generator=gen)
+    z = torch.randn(B, L, L, 64, generator=gen)
     q = torch.nn.functional.normalize(torch.randn(B, L, 4, generator=gen), dim=-1)
-    from oracle import pepflow_oracle as orc
-    rig = create_rigid(orc.quat_to_rot(q).to(dev), (torch.randn(B, L, 3, generator=gen) * 8.0).to(dev))
-    m = (torch.rand(B, L, generator=gen) > 0.15).float().to(dev)
-    outs = []
-    try:
-        for pack in (0, 1):
-            _lib.set_option("pack_impl", pack)
-            with torch.no_grad():
-                outs.append(model.ga_encoder.trunk["ipa_1"](s, z, rig, m).clone())
-    finally:
-        _lib.set_option("pack_impl", 1)
-    assert torch.equal(outs[0], outs[1])
+    rot = orc.quat_to_rot(q)
+    m = (torch.rand(B, L, generator=gen) > 0.15).float()
+    for shift in (0.0, 100.0):
+        trans = torch.randn(B, L, 3, generator=gen) * 8.0 + shift
+        ref = orc.ipa_forward(state_dict, "ga_encoder.trunk.ipa_1.", s, z, orc.Frames(trans, rot=rot), m)
+        rig = create_rigid(rot.to(dev), trans.to(dev))
+        with torch.no_grad():
+            out = model.ga_encoder.trunk["ipa_1"](s.to(dev), z.to(dev), rig, m.to(dev))
+        valid = m.bool()
+        assert rel_err(out.cpu()[valid], ref[valid]) < TOL, (shape, shift)
 
 
 @pytest.mark.parametrize("tag", ["ga_encoder_a", "ga_encoder_b"])

@@ -338,3 +338,16 @@ def test_sharded_sample_equals_single_gpu(state_dict):
     for n in range(steps):
         for k in full[n]:
             assert torch.equal(torch.cat([parts[0][n][k], parts[1][n][k]], 0), full[n][k]), (n, k)
+
+
+def test_embedders_every_pair_headline_shape(dev, model, state_dict, headline):
+    """EdgeEmbedder / NodeEmbedder kernels against the oracle on EVERY pair at L = 271, ill-conditioned dihedrals included:
+    the kernels reproduce the reference's CPU roundings of dihedral_from_four_points (pf_geom.cuh::dihedral4), so the
+    acos / sign conditioning no longer separates them (round 1 allowed 2e-3 on those pairs)."""
+    batch, enc, _ = headline
+    dbatch = {k: batch[k].to(dev) for k in BATCH_KEYS}
+    with torch.no_grad():
+        own = model.encode(dbatch)
+    e_node, e_edge = rel_err(own[4].cpu(), enc["node_embed"]), rel_err(own[5].cpu(), enc["edge_embed"])
+    print(f"embedders vs oracle at L=271, all pairs: node {e_node:.2e} edge {e_edge:.2e}")
+    assert e_node < 2e-5 and e_edge < 2e-5

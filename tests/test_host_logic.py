@@ -360,3 +360,53 @@ def test_reference_arm_does_not_import_the_product(tmp_path):
     import json
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["gpu_launches"] == 0
+
+
+def test_dihedral_rounding_model():
+    """The embedder kernels compute dihedral_from_four_points (geometry.py:296-313) with explicitly rounded operations in
+    the order PyTorch's CPU kernels use (pf_geom.cuh::dihedral4): cross = fma(a1, b2, -(a2 b1)), norm = sqrt(fma chain),
+    sums left to right.  This test pins that model against the installed torch build, bit for bit, on the layouts the
+    reference calls it with - if it ever fails, the kernel and the CPU reference differ again by the acos / sign
+    conditioning (1e-3 on ~1000 pairs per complex)."""
+    f32 = np.float32
+
+    def fma(x, y, z):
+        return (x.astype(np.float64) * y.astype(np.float64) + z.astype(np.float64)).astype(f32)
+
+    def cross(a, b):
+        c = lambda x, y, z, w: fma(x, y, -(z * w).astype(f32))
+        return np.stack([c(a[..., 1], b[..., 2], a[..., 2], b[..., 1]), c(a[..., 2], b[..., 0], a[..., 0], b[..., 2]),
+                         c(a[..., 0], b[..., 1], a[..., 1], b[..., 0])], -1)
+
+    def norm(u):
+        return np.sqrt(fma(u[..., 2], u[..., 2], fma(u[..., 1], u[..., 1], (u[..., 0] * u[..., 0]).astype(f32))))
+
+    def dot3(a, b):
+        m = (a * b).astype(f32)
+        return ((m[..., 0] + m[..., 1]).astype(f32) + m[..., 2]).astype(f32)
+
+    def model(p0, p1, p2, p3):
+        v0, v1, v2 = (p2 - p1).astype(f32), (p0 - p1).astype(f32), (p3 - p2).astype(f32)
+        u1, u2 = cross(v0, v1), cross(v0, v2)
+        n1, n2 = (u1 / norm(u1)[..., None]).astype(f32), (u2 / norm(u2)[..., None]).astype(f32)
+        return np.clip(dot3(n1, n2), f32(-0.999999), f32(0.999999)), np.sign(dot3(cross(v1, v2), v0))
+
+    def torch_ops(p0, p1, p2, p3):
+        v0, v1, v2 = p2 - p1, p0 - p1, p3 - p2
+        u1 = torch.cross(v0, v1, dim=-1)
+        n1 = u1 / torch.linalg.norm(u1, dim=-1, keepdim=True)
+        u2 = torch.cross(v0, v2, dim=-1)
+        n2 = u2 / torch.linalg.norm(u2, dim=-1, keepdim=True)
+        return ((n1 * n2).sum(-1).clamp(min=-0.999999, max=0.999999), torch.sign((torch.cross(v1, v2, dim=-1) * v0).sum(-1)))
+
+    g = torch.Generator().manual_seed(1)
+    for N, L in ((2, 140), (3, 37), (1, 8)):
+        pos = torch.randn(N, L, 3, 3, generator=g) * 6
+        pN, pCA, pC = pos[:, :, 0], pos[:, :, 1], pos[:, :, 2]
+        rows = lambda x: x[:, :, None].expand(N, L, L, 3)
+        cols = lambda x: x[:, None, :].expand(N, L, L, 3)
+        for args in ((rows(pC), cols(pN), cols(pCA), cols(pC)), (rows(pN), rows(pCA), rows(pC), cols(pN)),
+                     (pCA[:, :-1], pC[:, :-1], pN[:, 1:], pCA[:, 1:])):
+            x, s = torch_ops(*args)
+            xm, sm = model(*[a.numpy() for a in args])
+            assert np.array_equal(xm, x.numpy()) and np.array_equal(sm, s.numpy())
