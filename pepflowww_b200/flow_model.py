@@ -44,6 +44,10 @@ class FlowModel(nn.Module):
         self.k = self._interpolant_cfg.seqs.simplex_value
         if self.K != 20:
             raise ValueError("the Euler kernels are specialised to 20 residue classes")
+        # constants of the loss path as (non-persistent) buffers: no host->device copies inside forward(), which keeps
+        # a training iteration capturable in a CUDA graph; the state_dict is unchanged
+        self.register_buffer("_ideal_bb", torch.tensor(FlowModel._IDEAL_BB), persistent=False)
+        self.register_buffer("_torsions_mask", torsions_mask.clone(), persistent=False)
 
     # ------------------------------------------------------------------ reference helpers
     def encode(self, batch, autograd=False):
@@ -141,11 +145,9 @@ class FlowModel(nn.Module):
     # ------------------------------------------------------------------ training-style forward
     _IDEAL_BB = ((-0.525, 1.363, 0.0), (0.0, 0.0, 0.0), (1.526, 0.0, 0.0))  # N, CA, C in the backbone frame
 
-    @staticmethod
-    def _backbone_atoms(trans, rotmats):
+    def _backbone_atoms(self, trans, rotmats):
         """N, CA, C from frames - the [:, :, :3] slice of data/all_atom.py:39-45 (to_atom37)."""
-        ideal = torch.tensor(FlowModel._IDEAL_BB, device=trans.device, dtype=trans.dtype)
-        return torch.einsum("blij,aj->blai", rotmats, ideal) + trans[:, :, None, :]
+        return torch.einsum("blij,aj->blai", rotmats, self._ideal_bb.to(trans.dtype)) + trans[:, :, None, :]
 
     def forward(self, batch, *, noise=None):
         """Flow-matching losses (flow_model.py:111-227): returns the six-entry loss dict.
@@ -201,7 +203,7 @@ class FlowModel(nn.Module):
         pred_seqs_1 = torch.where(gen_b, pred_seqs_1, torch.clamp(seqs_1, 0, 19))
         pred_trans_1_c = pred_trans_1
 
-        norm_scale = 1 / (1 - torch.min(t[..., None], torch.tensor(cfg.t_normalization_clip, device=dev)))
+        norm_scale = 1 / (1 - torch.clamp(t[..., None], max=cfg.t_normalization_clip))
         gsum = torch.sum(gen_mask, dim=-1) + 1e-8
         trans_loss = torch.mean(torch.sum((pred_trans_1_c - trans_1_c) ** 2 * gen_mask[..., None], dim=(-1, -2)) / gsum)
 
@@ -217,7 +219,7 @@ class FlowModel(nn.Module):
                                     torch.clamp(seqs_1, 0, 19).reshape(-1), reduction="none").view(pred_seqs_1_prob.shape[:-1])
         seqs_loss = torch.mean(torch.sum(seqs_loss * gen_mask, dim=-1) / gsum)
 
-        aml = torsions_mask.to(dev)[pred_seqs_1.reshape(-1)].reshape(num_batch, num_res, -1)
+        aml = self._torsions_mask[pred_seqs_1.reshape(-1)].reshape(num_batch, num_res, -1)
         aml = torch.cat([aml, aml], dim=-1)
         aml = torch.logical_and(gen_b[..., None].bool(), aml)
         asum = torch.sum(aml, dim=(-1, -2)) + 1e-8
@@ -427,7 +429,7 @@ def _rot_vf_autograd(mat_t, mat_1):
     pref = torch.where(generic, th / (2.0 * torch.where(generic, sin_t, one)), torch.zeros_like(th))
     pref = torch.where(near_0, 0.5 / (1.0 - th.detach() ** 2 / 6.0), pref)
     out = v * pref[..., None]
-    if bool(near_pi.any()):
+    if rel.is_cuda or bool(near_pi.any()):           # on the GPU always (no host synchronisation: graph-capturable)
         diag = torch.diagonal(rel, dim1=-2, dim2=-1)
         M = (torch.eye(3, device=rel.device, dtype=rel.dtype) + rel) / 2.0
         axis = torch.sqrt(torch.clamp((1.0 + diag) / 2.0, min=1e-12))

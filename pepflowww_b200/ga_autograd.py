@@ -30,6 +30,13 @@ def _rot_to_quat(R):
                      m(0, 2) - m(2, 0), m(0, 1) + m(1, 0), m(1, 1) - m(0, 0) - m(2, 2), m(1, 2) + m(2, 1),
                      m(1, 0) - m(0, 1), m(0, 2) + m(2, 0), m(1, 2) + m(2, 1), m(2, 2) - m(0, 0) - m(1, 1)],
                     dim=-1).reshape(R.shape[:-2] + (4, 4)) / 3.0
+    if R.is_cuda:
+        # the kernel's rot -> quat (power iteration on the same K matrix, pf_rigid_update with a zero update): no cuSOLVER
+        # call, no host synchronisation - the training iteration stays capturable in a CUDA graph
+        from . import ops
+        z3 = torch.zeros(*R.shape[:-2], 3, device=R.device)
+        z6 = torch.zeros(*R.shape[:-2], 6, device=R.device)
+        return ops.rigid_update(None, R.contiguous(), z3, z6, torch.ones(R.shape[:-2], device=R.device))[0]
     return torch.linalg.eigh(K)[1][..., -1]
 
 

@@ -30,7 +30,8 @@ def sum_weighted_losses(losses, weights):
 
 def get_optimizer(cfg, model):
     if cfg.type == "adam":
-        return torch.optim.Adam(model.parameters(), lr=cfg.lr, weight_decay=cfg.weight_decay, betas=(cfg.beta1, cfg.beta2))
+        return torch.optim.Adam(model.parameters(), lr=cfg.lr, weight_decay=cfg.weight_decay, betas=(cfg.beta1, cfg.beta2),
+                                capturable=bool(cfg.get("capturable", False)))
     if cfg.type == "adamw":
         return torch.optim.AdamW(model.parameters(), lr=cfg.lr, weight_decay=cfg.weight_decay)
     raise NotImplementedError("Optimizer not supported: %s" % cfg.type)
@@ -59,6 +60,72 @@ def train_step(model, batch, optimizer, loss_weights, max_grad_norm):
     optimizer.step()
     optimizer.zero_grad()
     return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}, grad_norm
+
+
+class GraphedTrainStep:
+    """One training iteration (forward, weighted loss, backward, NaN rescue, clipping, optimizer step) captured ONCE in a
+    CUDA graph and replayed on a static input batch - the iteration is otherwise bound by the ~6,000 kernel launches of
+    the autograd formulation, not by arithmetic.  Needs: fixed batch shapes, an optimizer built with
+    capturable=True, and (with DistributedDataParallel) >= 11 eager iterations before capture so that DDP's bucket
+    views / reducer state are final; the NCCL all-reduces of the gradient buckets are captured as graph nodes."""
+
+    def __init__(self, model, optimizer, loss_weights, max_grad_norm, example_batch):
+        self.model, self.optimizer = model, optimizer
+        self.static = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in example_batch.items()}
+        dev = next(model.parameters()).device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        model.train()
+        with torch.cuda.stream(side):
+            optimizer.zero_grad(set_to_none=True)      # backward inside the capture allocates the grads in the graph's pool
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
+                loss_dict = model(self.static)
+                loss = sum_weighted_losses(loss_dict, loss_weights)
+                loss.backward()
+                for p in model.parameters():
+                    if p.grad is not None:
+                        torch.nan_to_num_(p.grad, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+                self.grad_norm = clip_grad_norm_(model.parameters(), max_grad_norm)
+                optimizer.step()
+            self.loss, self.loss_dict = loss.detach(), {k: v.detach() for k, v in loss_dict.items()}
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def __call__(self, batch):
+        for k, v in batch.items():
+            if isinstance(v, torch.Tensor):
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.loss_dict, self.grad_norm
+
+
+def nccl_overlap_summary(prof, iters):
+    """From a torch.profiler trace of `iters` iterations: device time of the NCCL kernels (DDP's gradient all-reduce)
+    per iteration and the share of it that runs while a compute kernel is executing on another stream."""
+    ker = [e for e in prof.events() if getattr(e, "device_type", None) is not None and "cuda" in str(e.device_type).lower()
+           and e.time_range is not None]
+    ivs = [(e.name, e.time_range.start, e.time_range.end) for e in ker]
+    nccl = [(a, b) for n, a, b in ivs if "nccl" in n.lower()]
+    comp = sorted((a, b) for n, a, b in ivs if "nccl" not in n.lower() and "memcpy" not in n.lower())
+    merged = []
+    for a, b in comp:
+        if merged and a <= merged[-1][1]:
+            merged[-1][1] = max(merged[-1][1], b)
+        else:
+            merged.append([a, b])
+    over = 0.0
+    for a, b in nccl:
+        for c, d in merged:
+            if d <= a:
+                continue
+            if c >= b:
+                break
+            over += min(b, d) - max(a, c)
+    total = sum(b - a for a, b in nccl)
+    names = sorted({n for n, _, _ in ivs if "nccl" in n.lower()})
+    return {"nccl_kernel_ms_per_iter": total / 1e3 / max(1, iters), "nccl_launches_per_iter": len(nccl) / max(1, iters),
+            "overlapped_with_compute": (over / total) if total > 0 else None, "kernels": names[:4],
+            "compute_kernel_launches_per_iter": len(comp) / max(1, iters)}
 
 
 def inf_iterator(iterable):
@@ -105,6 +172,10 @@ def main(argv=None):
     ap.add_argument("--save", default=None)
     ap.add_argument("--resume", default=None)
     ap.add_argument("--dataset-size", type=int, default=4096, help="synthetic complexes per epoch")
+    ap.add_argument("--graph", action="store_true", help="capture the iteration in a CUDA graph (fixed batch shapes)")
+    ap.add_argument("--tf32", action="store_true", help="TF32 tensor-core matmuls in the autograd path (not the reference's numerics)")
+    ap.add_argument("--profile", type=int, default=0, help="profile this many extra iterations (NCCL time / overlap)")
+    ap.add_argument("--out", default=None, help="append the JSON line to this file")
     args = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -114,10 +185,21 @@ def main(argv=None):
     dev = torch.device("cuda", local_rank)
     config, _ = load_config(args.config) if args.config else load_config()
     seed_all(config.train.seed + 100 * rank)
+    if args.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
     if world > 1:
-        dist.init_process_group(backend="nccl")
+        dist.init_process_group(backend="nccl", device_id=dev)
     net = FlowModel(config.model).to(dev)
-    model = DDP(net, device_ids=[local_rank]) if world > 1 else net
+    if world > 1 and args.graph:                        # DDP for graph capture is built on a side stream
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            model = DDP(net, device_ids=[local_rank], broadcast_buffers=False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+    else:
+        model = DDP(net, device_ids=[local_rank], broadcast_buffers=False) if world > 1 else net
+    if args.graph:
+        config.train.optimizer["capturable"] = True
     optimizer = get_optimizer(config.train.optimizer, model)
     scheduler = get_scheduler(config.train.scheduler, optimizer)
     bs = args.batch_size or config.train.batch_size
@@ -133,30 +215,67 @@ def main(argv=None):
     train_iterator = inf_iterator(make_loader(dataset, bs, rank, world, seed=config.train.seed))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     last = None
-    for it in range(it_first, it_first + args.warmup + args.iters):
-        if it == it_first + args.warmup:
+    warmup = max(args.warmup, 11) if (args.graph and world > 1) else args.warmup
+    graphed = None
+
+    def one_iteration():
+        batch = recursive_to(next(train_iterator), dev)
+        if graphed is not None:
+            return graphed(batch)
+        return train_step(model, batch, optimizer, config.train.loss_weights, config.train.max_grad_norm)
+
+    for it in range(it_first, it_first + warmup + args.iters):
+        if it == it_first + warmup:
+            if args.graph:
+                graphed = GraphedTrainStep(model, optimizer, config.train.loss_weights, config.train.max_grad_norm,
+                                           recursive_to(next(train_iterator), dev))
+                graphed(recursive_to(next(train_iterator), dev))          # one replay outside the timed region
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             ev0.record()
-        batch = recursive_to(next(train_iterator), dev)
-        last = train_step(model, batch, optimizer, config.train.loss_weights, config.train.max_grad_norm)
+        last = one_iteration()
     ev1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([ev0.elapsed_time(ev1) / max(1, args.iters)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    nccl = None
+    if args.profile > 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(args.profile):
+                one_iteration()
+            torch.cuda.synchronize()
+        if rank == 0:
+            nccl = nccl_overlap_summary(prof, args.profile)
     if rank == 0:
         if args.save:
-            torch.save(checkpoint_dict(config, model, optimizer, scheduler, it_first + args.warmup + args.iters - 1),
+            torch.save(checkpoint_dict(config, model, optimizer, scheduler, it_first + warmup + args.iters - 1),
                        args.save)
-        print(json.dumps({"metric": "training samples/sec (flow-matching loss, fwd+bwd+Adam)", "unit": "samples/s",
-                          "value": bs * world / (float(ms) / 1e3), "ms_per_iter": float(ms), "n_gpus": world,
-                          "batch_per_gpu": bs, "residues": args.pocket + args.peptide, "loss": float(last[0]),
-                          "grad_norm": float(last[2]), "time": time.strftime("%Y-%m-%d %H:%M:%S")}))
+        line = json.dumps({"metric": "training samples/sec (flow-matching loss, fwd+bwd+Adam)", "unit": "samples/s",
+                           "value": bs * world / (float(ms) / 1e3), "ms_per_iter": float(ms), "n_gpus": world,
+                           "batch_per_gpu": bs, "residues": args.pocket + args.peptide,
+                           "padded_residues": -(-(args.pocket + args.peptide) // 8) * 8, "iters": args.iters,
+                           "cuda_graph": bool(args.graph), "tf32_matmul": bool(args.tf32), "loss": float(last[0]),
+                           "grad_norm": float(last[2]), "ddp_allreduce": nccl, "time": time.strftime("%Y-%m-%d %H:%M:%S")})
+        print(line)
+        if args.out:
+            with open(args.out, "a") as fh:
+                fh.write(line + "\n")
     if world > 1:
+        if args.graph:
+            # Measured on the 8 x B200 box (profiles/r2_train_cfg5_ddp.jsonl): with the gradient all-reduces captured in
+            # the graph, process-group teardown never returns (every rank had already printed / written its results).
+            # Drop the graph, meet once more, and leave without the NCCL destructor.
+            import sys
+            graphed = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
-if __name__ == "__main__":
-    main()
+if __name__

@@ -12,9 +12,20 @@ def time_frequencies(embedding_dim=128, max_positions=2056):
     return torch.exp(torch.arange(half, dtype=torch.float32) * -step)
 
 
+_FREQ_CACHE = {}
+
+
+def _frequencies_on(device, embedding_dim, max_positions):
+    """Host-computed table, uploaded once per device (no host->device copy per call: CUDA-graph capturable)."""
+    key = (str(device), embedding_dim, max_positions)
+    if key not in _FREQ_CACHE:
+        _FREQ_CACHE[key] = time_frequencies(embedding_dim, max_positions).to(device)
+    return _FREQ_CACHE[key]
+
+
 def get_time_embedding(timesteps, embedding_dim, max_positions=2000):
     assert len(timesteps.shape) == 1
-    freqs = time_frequencies(embedding_dim, max_positions).to(timesteps.device)
+    freqs = _frequencies_on(timesteps.device, embedding_dim, max_positions)
     arg = (timesteps * max_positions).float()[:, None] * freqs[None, :]
     emb = torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
     if embedding_dim % 2 == 1:
