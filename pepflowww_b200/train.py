@@ -278,4 +278,5 @@ def main(argv=None):
         dist.destroy_process_group()
 
 
-if __name__
+if __name__ == "__main__":
+    main()
