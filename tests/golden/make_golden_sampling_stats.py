@@ -5,8 +5,12 @@ rotation-matrix RMSD and amino-acid recovery of the final state over the generat
 
     python tests/golden/make_golden_sampling_stats.py
 
-32 synthetic complexes (20-residue pocket, 8-residue peptide, the generator of pepflowww_b200.pep_dataloader) x 8 noise
-draws = 256 samples; writes tests/golden/sampling_stats.npz.  The GPU test (tests/test_gpu_parity_r2.py::
+32 synthetic complexes (20-residue pocket, 8-residue peptide, the generator of pepflowww_b200.pep_dataloader) x 16 noise
+draws = 512 samples; writes tests/golden/sampling_stats.npz.  Besides the three realised metrics it records `p_gt`, the
+mean softmax probability the final denoiser call assigns to the true residue type over the generated residues (the
+EXPECTATION of the amino-acid recovery, read from the logits of the last GAEncoder.forward call through a forward hook -
+the reference code itself is not modified): the realised recovery of 8 residues is a coarse count (binomial noise
++-0.014 per draw of 256 residues), its expectation is what separates two samplers.  The GPU test (tests/test_gpu_parity_r2.py::
 test_200_step_sampling_statistics) draws the same number of samples from the CUDA path with its own RNG (Philox) and
 compares the distributions (means within 4 standard errors, two-sample Kolmogorov-Smirnov statistic).
 """
@@ -29,7 +33,7 @@ from pepflowww_b200.pep_dataloader import synthetic_batch  # noqa: E402
 from pepflowww_b200.utils import deterministic_state_dict  # noqa: E402
 
 WEIGHT_SEED = 114514
-N_COMPLEX, POCKET, PEPTIDE, DRAWS, STEPS, DATA_SEED = 32, 20, 8, 8, 200, 31
+N_COMPLEX, POCKET, PEPTIDE, DRAWS, STEPS, DATA_SEED = 32, 20, 8, 16, 200, 31
 
 
 def metrics(final, gm):
@@ -52,14 +56,25 @@ def main():
     torch.set_grad_enabled(False)
     batch = synthetic_batch(N_COMPLEX, POCKET, PEPTIDE, seed=DATA_SEED)
     gm = batch["generate_mask"]
-    out = {"tran": [], "rot": [], "aar": []}
+    out = {"tran": [], "rot": [], "aar": [], "p_gt": []}
+    last = {}
+    inner = model.ga_encoder.forward
+
+    def recording_forward(*a, **k):
+        res = inner(*a, **k)
+        last["logits"] = res[3]
+        return res
+
+    model.ga_encoder.forward = recording_forward
     t0 = time.time()
     for d in range(DRAWS):
         np.random.seed(1000 + d)
         torch.manual_seed(1000 + d)
         traj = model.sample(batch, num_steps=STEPS)
         tran, rot, aar = metrics(traj[-1], gm)
+        p = torch.softmax(last["logits"], -1).gather(-1, batch["aa"].clamp(0, 19)[..., None])[..., 0]
         out["tran"].append(tran); out["rot"].append(rot); out["aar"].append(aar)
+        out["p_gt"].append((p * gm).sum(-1) / (gm.sum(-1).float() + 1e-8))
         print(f"draw {d}: tran {float(tran.mean()):.3f} rot {float(rot.mean()):.3f} aar {float(aar.mean()):.3f} "
               f"({time.time() - t0:.0f} s)", flush=True)
     arrs = {k: torch.stack(v).numpy() for k, v in out.items()}       # [DRAWS, N_COMPLEX]
