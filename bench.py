@@ -225,6 +225,18 @@ def ncu_traffic(kernel, impl, B, L):
     return None
 
 
+def ncu_traffic_source(kernel, impl, B, L):
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            table = json.load(f)
+    except (OSError, ValueError):
+        return None
+    for e in table.get(kernel, []):
+        if e.get("impl") == impl and e.get("B") == B and e.get("L") == L:
+            return e.get("source")
+    return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     from pepflowww_b200 import _lib
@@ -320,6 +332,7 @@ def run_ours(args):
         roofline = {"kernel": "ipa_attention", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak,
                     "traffic": ncu_traffic("ipa_attention", _lib.get_option("ipa_impl"), B, L), "peak_source": peak_src,
+                    "traffic_source": ncu_traffic_source("ipa_attention", _lib.get_option("ipa_impl"), B, L),
                     "avg_launch_ms": ipa_ms / ipa_n, "launches": ipa_n, "share_of_step": ipa_ms / prof_ms,
                     "algorithmic_bytes_per_launch": ipa_bytes,
                     "timed": "CUDA events around every launch inside the timed region" if not use_graph else

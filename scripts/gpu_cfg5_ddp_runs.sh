@@ -1,3 +1,6 @@
+# The commands of the 8 x B200 call of round 2 (sharded-sample equality test, cfg5 DDP training at 2 / 4 / 8 GPUs, eager with
+# the NCCL overlap profile and with the whole-iteration CUDA graph).  Results: profiles/r2_train_cfg5_ddp.jsonl,
+# profiles/r2_pytest_sharded_2gpu.log.  Run under: gpurun --gpus 8 -- bash scripts/gpu_cfg5_ddp_runs.sh
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out/r2g
 nvidia-smi -L | head -8

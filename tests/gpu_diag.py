@@ -24,7 +24,7 @@ def rel(a, b):
 
 def main():
     edge_impl, gemm_impl = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (0, 0)
-    ipa_impl = int(os.environ.get("IPA_IMPL", "1"))
+    ipa_impl = int(os.environ.get("IPA_IMPL", "4"))
     _lib.set_option("edge_impl", edge_impl)
     _lib.set_option("gemm_impl", gemm_impl)
     _lib.set_option("ipa_impl", ipa_impl)

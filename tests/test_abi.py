@@ -98,3 +98,34 @@ def test_plain_c_consumer(tmp_path):
     r = subprocess.run([exe, _lib.LIB_PATH], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "abi ok" in r.stdout
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """pf_sampler / pf_ga_weights as C sees them (gcc, offsetof / sizeof) == the ctypes Structures the Python mirror passes:
+    a field added on one side only would shift every pointer after it."""
+    import shutil
+    import subprocess
+    from pepflowww_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    fields = [n for n, _ in _lib.Sampler._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "pepflow_b200.h"', 'int main(void) {',
+            '  printf("sizeof_sampler %zu\\n", sizeof(pf_sampler));',
+            '  printf("sizeof_weights %zu\\n", sizeof(pf_ga_weights));',
+            '  printf("w_g %zu\\n", offsetof(pf_ga_weights, g));', '  printf("w_blk %zu\\n", offsetof(pf_ga_weights, blk));',
+            '  printf("w_prepacked %zu\\n", offsetof(pf_ga_weights, prepacked));',
+            '  printf("w_prepacked_bytes %zu\\n", offsetof(pf_ga_weights, prepacked_bytes));']
+    prog += [f'  printf("{f} %zu\\n", offsetof(pf_sampler, {f}));' for f in fields]
+    prog += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = str(tmp_path / "layout")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    out = dict(line.split() for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out["sizeof_sampler"]) == ctypes.sizeof(_lib.Sampler)
+    for f in fields:
+        assert int(out[f]) == getattr(_lib.Sampler, f).offset, f
+    assert int(out["sizeof_weights"]) == ctypes.sizeof(_lib.GaWeights)
+    for c_name, py_name in (("w_g", "g"), ("w_blk", "blk"), ("w_prepacked", "prepacked"), ("w_prepacked_bytes", "prepacked_bytes")):
+        assert int(out[c_name]) == getattr(_lib.GaWeights, py_name).offset, py_name

@@ -544,7 +544,13 @@ def test_edge_embed_kernel(dev, model, state_dict):
     print("edge_embed kernel (well-conditioned pairs, all pairs, share well-conditioned): " +
           "; ".join("%s %.2e %.2e %.2f" % ((k,) + v) for k, v in res.items()))
     for k, (e_ok, e_all, share) in res.items():
-        assert e_ok < TOL and e_all < 2e-3 and share > 0.5, (k, e_ok, e_all, share)
+        assert e_ok < TOL and share > 0.5, (k, e_ok, e_all, share)
+        # Against the reference's CPU outputs every pair holds (the kernel reproduces the CPU roundings of the dihedrals;
+        # test_embedders_every_pair_headline_shape pins 2e-5 at L = 271).  The torch formulation on the GPU rounds
+        # differently: on near-planar pairs its acos argument / dihedral sign may legitimately disagree, so only the
+        # well-conditioned pairs are compared with it.
+        if k != "L=271 vs torch ops":
+            assert e_all < 2e-3, (k, e_ok, e_all, share)
 
 
 def test_sample_free_running_flags_and_shapes(dev, model):
