@@ -410,3 +410,26 @@ def test_dihedral_rounding_model():
             x, s = torch_ops(*args)
             xm, sm = model(*[a.numpy() for a in args])
             assert np.array_equal(xm, x.numpy()) and np.array_equal(sm, s.numpy())
+
+
+def test_nccl_overlap_summary_interval_arithmetic():
+    """train.nccl_overlap_summary (the source of the NCCL kernel time / overlap figures of DESIGN.md section 7): NCCL kernel
+    intervals intersected with the union of compute-kernel intervals, per iteration."""
+    from types import SimpleNamespace as NS
+    from pepflowww_b200.train import nccl_overlap_summary
+
+    def ev(name, a, b, dev="DeviceType.CUDA"):
+        return NS(name=name, device_type=dev, time_range=NS(start=a, end=b))
+
+    events = [ev("gemm_a", 0, 100), ev("gemm_b", 50, 150),                  # union [0, 150]
+              ev("gemm_c", 300, 400),
+              ev("ncclDevKernel_AllReduce_Sum_f32_RING_LL", 120, 320),      # 200 us: overlaps [120,150] + [300,320] = 50 us
+              ev("ncclDevKernel_AllReduce_Sum_f32_RING_LL", 1000, 1100),    # 100 us, no compute underneath
+              ev("Memcpy DtoD", 1000, 1100),                                # copies do not count as compute
+              ev("cpu_op", 0, 5000, dev="DeviceType.CPU")]
+    out = nccl_overlap_summary(NS(events=lambda: events), iters=2)
+    assert abs(out["nccl_kernel_ms_per_iter"] - 0.150) < 1e-9               # (200 + 100) us / 2 iterations
+    assert out["nccl_launches_per_iter"] == 1.0
+    assert abs(out["overlapped_with_compute"] - 50.0 / 300.0) < 1e-9
+    assert out["compute_kernel_launches_per_iter"] == 1.5
+    assert nccl_overlap_summary(NS(events=lambda: events[:3]), iters=1)["overlapped_with_compute"] is None
