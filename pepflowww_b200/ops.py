@@ -324,3 +324,27 @@ def torsion_angles(pos_atoms, aa, tables):
     check(lib.pf_torsion_angles(ptr(pos), ptr(_c(aa, I64), I64), ptr(tables["chi_atoms"], torch.int32), ptr(tor),
                                 ptr(mask, U8), n, pos.shape[-2], stream()))
     return tor, mask.view(torch.bool)
+
+
+# ---- device scoping -----------------------------------------------------------------------------------------------------
+# Every wrapper above launches on "torch's current stream", which only means the tensors' stream while their device is the
+# current one.  Wrap each public op so that a call with tensors on another device runs under torch.cuda.device(that device)
+# (and therefore on that device's current stream); on the usual single-device process this is one integer comparison.
+def _device_scoped(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and getattr(_fn, "__module__", None) == __name__ and not _name.startswith("_"):
+        globals()[_name] = _device_scoped(_fn)
+del _name, _fn
