@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(P3_THREADS) ipa_packq_kernel(IpaPack3Args a) {
   }
 }
 
-// ---- persistent, double-buffered blob packer ("pack_impl" = 1, default): the K' / V' part of ipa_pack3 with the
+// ---- persistent, double-buffered blob packer: the K' / V' fragments, key bias, key mask and key translations, with the
 // rows of the NEXT key tile landing in shared memory (bulk copies on an mbarrier) while the current tile is being cut
 // into fragments, one CTA per SM walking the tiles with stride gridDim.x.  The Q' tiles keep the kernel above.
 constexpr int P4_THREADS = 768;                                    // one CTA per SM: 24 warps cut fragments
