@@ -184,19 +184,35 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+    # K timed + W warm-up Euler iterations exactly as asked (bounded only against a run of hours: <= 60 iterations of a
+    # 4-complex sample, ~1 s each on the GPU box's host cores)
+    steps, warmup = max(1, min(args.steps, 60)), max(1, min(args.warmup, 10))
     cb = cpu_baseline(args, steps, warmup)
+    _, weights = load_weights()
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"],
             "unit": "peptides/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{cfg_name(args)}: {args.batch} complexes/GPU x {args.gpus} GPU, {args.pocket}-res pocket / "
-                                   f"{args.peptide}-res peptide (L={args.pocket + args.peptide}), {EULER_STEPS} Euler steps",
-                       "step": f"bounded CPU sample: Euler iterations over {args.cpu_batch} complexes of the same shape on "
-                               f"the host cores, extrapolated per complex"},
+            "config": workload_config(args, args.gpus, weights),
+            "run": {"step": f"bounded CPU sample: one Euler iteration over {min(args.cpu_batch, args.batch)} complexes of the same "
+                            f"shape on the host cores (all threads), extrapolated per complex; rank 0 only"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "peptides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus, weights):
+    """The `config` object of the JSON line: ONLY what defines the workload, built by the same function in both arms so
+    that the driver sees the same configuration for `--impl ours` and `--impl reference` (how each arm runs it is in the
+    top-level `run` object)."""
+    B, L = args.batch, args.pocket + args.peptide
+    z_bytes = B * L * L * 256
+    return {"workload": f"{cfg_name(args)}: {B} complexes/GPU x {n_gpus} GPU, {args.pocket}-res pocket / "
+                        f"{args.peptide}-res peptide (L={L}), {EULER_STEPS} Euler steps",
+            "global_batch": B * n_gpus, "euler_steps": EULER_STEPS,
+            "parallelism": f"complexes sharded over {n_gpus} GPU(s), no collective", "weights": weights,
+            "l2": ("inputs larger than L2 (pair tensor z = %.2f GB per pass and GPU)" % (z_bytes / 1e9)) if z_bytes > 126e6 else
+                  ("pair tensor z = %.1f MB per pass fits L2 (small-batch stand-in; every pass rewrites it)" % (z_bytes / 1e6))}
 
 
 def cfg_name(args):
@@ -424,20 +440,14 @@ def run_ours(args):
         line = {"metric": METRIC,
                 "value": value, "unit": "peptides/s", "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{cfg_name(args)}: {B} complexes/GPU x {n_gpus} GPU, {args.pocket}-res pocket / "
-                                       f"{args.peptide}-res peptide (L={L}), {EULER_STEPS} Euler steps",
-                           "step": "one Euler iteration (GAEncoder.forward + post-processing + manifold update = one "
-                                   "pf_sampler_step call) over the per-GPU batch, state resident in HBM; value = complexes "
-                                   "/ (200 x step time); sample_wall = the whole 200-iteration sample measured; e2e = the "
-                                   "same from / to host memory (the headline)",
-                           "global_batch": B * n_gpus, "parallelism": f"complexes sharded over {n_gpus} GPU(s), no collective",
-                           "weights": weights, "graph_replay_in_timed_steps": use_graph,
-                           "launches_per_step": (launches // K) if K else None,
-                           "l2": "inputs larger than L2 (pair tensor z = %.2f GB per pass)" % (B * L * L * 256 / 1e9)
-                                 if B * L * L * 256 > 126e6 else
-                                 "pair tensor z = %.1f MB per pass fits L2 (small-batch stand-in; every pass rewrites it)"
-                                 % (B * L * L * 256 / 1e6),
-                           "kernels": {k: _lib.get_option(k) for k in ("edge_impl", "gemm_impl", "ipa_impl", "edge_terms")}},
+                "config": workload_config(args, n_gpus, weights),
+                "run": {"step": "one Euler iteration (GAEncoder.forward + post-processing + manifold update = one "
+                                "pf_sampler_step call) over the per-GPU batch, state resident in HBM; value = complexes "
+                                "/ (200 x step time); sample_wall = the whole 200-iteration sample measured; e2e = the "
+                                "same from / to host memory (the headline)",
+                        "graph_replay_in_timed_steps": use_graph, "launches_per_step": (launches // K) if K else None,
+                        "kernels": {k: _lib.get_option(k) for k in ("edge_impl", "gemm_impl", "ipa_impl", "edge_terms",
+                                                                    "mma_order")}},
                 "clocks": clk, "gpu_launches": launches, "e2e": e2e, "sample_wall": sample_wall, "roofline": roofline,
                 "roofline_edge_transition": roofline_edge, "cpu_baseline": cb}
         print(json.dumps(line), flush=True)
