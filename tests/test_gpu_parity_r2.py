@@ -372,6 +372,31 @@ def test_embedders_every_pair_headline_shape(dev, model, state_dict, headline):
     assert e_node < 2e-5 and e_edge < 2e-5
 
 
+def test_rigid_apply_and_ipa_points_vs_oracle(dev):
+    """Rigid.apply / invert_apply (openfold/utils/rigid_utils.py:1124-1150, row a14) as a seam of their own: pf_ipa_points
+    (the projection's point outputs moved to the global frame, ipa_pytorch.py:360-387) against the oracle's formula, and
+    the Python mirror's Rigid.apply / invert_apply against orc.rot_apply, round trip included."""
+    from pepflowww_b200 import ops
+    from pepflowww_b200.rigid import create_rigid
+    g = torch.Generator().manual_seed(12)
+    B, L = 3, 37
+    proj = torch.randn(B, L, 3744, generator=g)
+    rot = orc.quat_to_rot(torch.nn.functional.normalize(torch.randn(B, L, 4, generator=g), dim=-1))
+    trans = torch.randn(B, L, 3, generator=g) * 10
+    pts = ops.ipa_points(proj.to(dev), rot.to(dev), trans.to(dev)).cpu()                  # [B, L, 8 heads, 28, 3]
+    q_loc = proj[..., 3072:3264].reshape(B, L, 3, 8, 8).permute(0, 1, 3, 4, 2)            # x | y | z planes, head-major
+    kv_loc = proj[..., 3264:3744].reshape(B, L, 3, 8, 20).permute(0, 1, 3, 4, 2)
+    loc = torch.cat([q_loc, kv_loc], dim=3)                                               # q (8) | k (8) | v (12) points
+    ref = torch.einsum("blij,blhnj->blhni", rot, loc) + trans[:, :, None, None, :]
+    assert pts.shape == ref.shape and rel_err(pts, ref) < 1e-6
+    rig = create_rigid(rot.to(dev), trans.to(dev))
+    x = torch.randn(B, L, 3, generator=g) * 5
+    y = rig.apply(x.to(dev))
+    assert rel_err(y.cpu(), orc.rot_apply(rot, x) + trans) < 1e-6
+    assert rel_err(rig.invert_apply(y).cpu(), x) < 1e-5
+    assert rel_err(rig.invert_apply(x.to(dev)).cpu(), torch.einsum("blji,blj->bli", rot, x - trans)) < 1e-6
+
+
 def _ks_statistic(a, b):
     """two-sample Kolmogorov-Smirnov statistic sup |F_a - F_b|"""
     a, b = np.sort(np.asarray(a, dtype=np.float64)), np.sort(np.asarray(b, dtype=np.float64))
