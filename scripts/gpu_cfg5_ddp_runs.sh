@@ -4,7 +4,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out/r2g
 nvidia-smi -L | head -8
-timeout 600 python -m pytest tests/test_gpu_parity_r2.py -q -s -k "sharded" 2>&1 | tail -4 | tee gpurun_out/r2g/pytest_sharded.log
+timeout 600 python -m pytest tests/test_gpu_headline_parity.py -q -s -k "sharded" 2>&1 | tail -4 | tee gpurun_out/r2g/pytest_sharded.log
 run() { N=$1; shift; timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+N)) -m pepflowww_b200.train --batch-size 32 --pocket 128 --peptide 12 --out gpurun_out/r2g/train_cfg5.jsonl "$@" 2>&1 | grep -v "^W\|warn\|^$" | tail -3; }
 run 2 --iters 6 --warmup 2 --profile 2
 run 2 --iters 6 --warmup 2 --graph

@@ -10,7 +10,7 @@ draws = 512 samples; writes tests/golden/sampling_stats.npz.  Besides the three 
 mean softmax probability the final denoiser call assigns to the true residue type over the generated residues (the
 EXPECTATION of the amino-acid recovery, read from the logits of the last GAEncoder.forward call through a forward hook -
 the reference code itself is not modified): the realised recovery of 8 residues is a coarse count (binomial noise
-+-0.014 per draw of 256 residues), its expectation is what separates two samplers.  The GPU test (tests/test_gpu_parity_r2.py::
++-0.014 per draw of 256 residues), its expectation is what separates two samplers.  The GPU test (tests/test_gpu_zz_sampling_statistics.py::
 test_200_step_sampling_statistics) draws the same number of samples from the CUDA path with its own RNG (Philox) and
 compares the distributions (means within 4 standard errors, two-sample Kolmogorov-Smirnov statistic).
 """
