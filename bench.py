@@ -122,7 +122,18 @@ def load_weights():
     import benchdata
     ckpt = os.environ.get("PEPFLOW_CKPT")
     if ckpt and os.path.exists(ckpt):
-        sd = torch.load(ckpt, map_location="cpu", weights_only=False)["model"]
+        # the reference pickles its config as easydict.EasyDict (not in this image): a dict stand-in for the load
+        import types
+        shim = None
+        if "easydict" not in sys.modules:
+            shim = types.ModuleType("easydict")
+            shim.EasyDict = type("EasyDict", (dict,), {"__module__": "easydict"})
+            sys.modules["easydict"] = shim
+        try:
+            sd = torch.load(ckpt, map_location="cpu", weights_only=False)["model"]
+        finally:
+            if shim is not None:
+                sys.modules.pop("easydict", None)
         return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}, os.path.basename(ckpt)
     return benchdata.reference_state_dict(WEIGHT_SEED), f"deterministic random init (seed {WEIGHT_SEED}, non-zero 'final' layers)"
 
